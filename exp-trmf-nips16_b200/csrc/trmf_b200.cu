@@ -1,0 +1,772 @@
+// trmf_b200.cu -- host driver + C ABI of the B200-native TRMF ALS solver.
+//
+// Built twice (-DValueType=float / double) into trmf_float32.so / trmf_float64.so,
+// mirroring the reference's two libraries (corelib/Makefile:32-33).  The ALS loop
+// and the TRON/CG control flow follow the reference's *semantics*
+// (trmf.cpp:599-694, rf_tron.h:135-254,412-505); every array lives in HBM for the
+// whole call and every inner update is a CUDA kernel from the .cuh files next to
+// this one.  There is no CPU compute path.
+#include "../../include/trmf_b200.h"
+#include "common.cuh"
+#include "f_update.cuh"
+#include "f_update_tiled.cuh"
+#include "x_update.cuh"
+#include "lag_update.cuh"
+#include "dense.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#define TRMF_B200_VERSION "trmf-b200 0.1 (sm_100a)"
+
+// --------------------------------------------------------------------------
+// error plumbing
+// --------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+static int fail(const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    fprintf(stderr, "[trmf-b200 ERROR]: %s\n", buf);
+    fflush(stderr);
+    return 1;
+}
+
+#define CUDA_TRY(...)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (__VA_ARGS__);                                                   \
+        if (e__ != cudaSuccess)                                                            \
+            return fail("%s failed at %s:%d: %s", #__VA_ARGS__, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+
+// --------------------------------------------------------------------------
+// session
+// --------------------------------------------------------------------------
+struct trmf_b200_session {
+    int device = 0;
+    int num_sms = 148;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+
+    size_t T = 0, n = 0, nnz = 0;
+    int k = 0, L = 0, mid = 0;
+    bool missing = true;          // ARR_LS_MISSING (31) vs ARR_LS_FULL (30), trmf.cpp:717
+    bool sparse_storage = true;
+    int dense_type = 0;           // TRMF_DENSE_ROWMAJOR / COLMAJOR when !sparse_storage
+
+    // Y in HBM: both orientations when sparse
+    uint64_t *row_ptr = nullptr, *col_ptr = nullptr;
+    uint32_t *col_idx = nullptr, *row_idx = nullptr;
+    V *val_t = nullptr, *val = nullptr;
+    V *Yd = nullptr;
+    bool own_Y = false;
+
+    // factors
+    V *W = nullptr, *H = nullptr, *th = nullptr;
+    bool own_factors = false;
+    std::vector<uint32_t> lags;
+    uint32_t *lags_dev = nullptr;
+
+    // X-update work space (TRON's s, r, w_new, g, d, Hd: rf_tron.h:52-54)
+    V *g = nullptr, *s = nullptr, *r = nullptr, *d = nullptr, *Hd = nullptr, *wnew = nullptr;
+    double *rho = nullptr;
+    double *scal = nullptr, *part = nullptr;
+    unsigned *ticket = nullptr;
+    double *h_scal = nullptr;     // pinned mirror of `scal`
+
+    // dense-mode work space
+    V *YH = nullptr;              // T x k
+    V *tmp_nk = nullptr;          // n x k (sparse-storage dense mode)
+    double *HTH = nullptr, *WTW = nullptr, *YtW = nullptr, *Cpart = nullptr;
+    size_t Cpart_elems = 0;
+    double trYTY = 0.0;
+
+    // lag update work space
+    double *lag_partial = nullptr;
+    int lag_chunk = 0, lag_nchunks = 0;
+
+    // multi-GPU
+    int rank = 0, world = 1;
+    void *nccl_comm = nullptr;
+
+    double lambdaI = 0.1, lambdaAR = 0.1, lambdaLag = 0.1;
+
+    // stats
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    double st_cg = 0, st_acc = 0, st_f = 0, st_fnew = 0, st_gnorm = 0, st_prered = 0, st_actred = 0;
+    double ms_f = 0, ms_x = 0, ms_lag = 0, ms_fk = 0;
+    unsigned long long launches = 0;
+    double st_delta = 0, st_rnorm = 0;
+};
+typedef trmf_b200_session S;
+
+// `kern` may be a parenthesised template-id; it is bound to a pointer first.
+#define LAUNCH(s, kern, grid, block, smem, ...)                                           \
+    do {                                                                                   \
+        auto kfn__ = kern;                                                                 \
+        kfn__<<<(grid), (block), (smem), (s)->stream>>>(__VA_ARGS__);                      \
+        (s)->launches++;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess)                                                            \
+            return fail("launch of %s failed at %s:%d: %s", #kern, __FILE__, __LINE__, cudaGetErrorString(e__)); \
+    } while (0)
+
+static inline unsigned ew_grid(const S *s, size_t n, int threads = 256) {
+    size_t b = (n + threads - 1) / threads;
+    size_t cap = (size_t)s->num_sms * 8;
+    return (unsigned)std::max<size_t>(1, std::min(b, cap));
+}
+
+template <typename T>
+static int dev_alloc(T **p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+    return 0;
+}
+
+// --------------------------------------------------------------------------
+// creation / destruction
+// --------------------------------------------------------------------------
+static int session_common_init(S *s) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
+    s->num_sms = prop.multiProcessorCount;
+    if (prop.major < 10)
+        return fail("device %d (%s, sm_%d%d) is not a Blackwell (sm_100a) GPU; this library has no other code path",
+                    s->device, prop.name, prop.major, prop.minor);
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+    const size_t tk = s->T * (size_t)s->k;
+    if (dev_alloc(&s->g, tk) || dev_alloc(&s->s, tk) || dev_alloc(&s->r, tk) || dev_alloc(&s->d, tk) ||
+        dev_alloc(&s->Hd, tk) || dev_alloc(&s->wnew, tk) || dev_alloc(&s->rho, tk))
+        return 1;
+    if (dev_alloc(&s->scal, SC_COUNT) || dev_alloc(&s->part, 8192) || dev_alloc(&s->ticket, 4)) return 1;
+    CUDA_TRY(cudaMemsetAsync(s->scal, 0, SC_COUNT * sizeof(double), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned), s->stream));
+    CUDA_TRY(cudaMallocHost((void **)&s->h_scal, SC_COUNT * sizeof(double)));
+    if (dev_alloc(&s->lags_dev, s->lags.size())) return 1;
+    CUDA_TRY(cudaMemcpyAsync(s->lags_dev, s->lags.data(), s->lags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
+    // lag update: chunk the window so that (chunk + mid) fp64 values fit in shared memory
+    {
+        const size_t budget = 160 * 1024 / sizeof(double);
+        if ((size_t)s->mid + 256 > budget)
+            return fail("max lag %d too large for the lag_val kernel's shared-memory staging (limit %zu)", s->mid, budget - 256);
+        size_t chunk = std::min<size_t>(4096, budget - s->mid);
+        size_t win = s->T > (size_t)s->mid ? s->T - s->mid : 0;
+        // enough CTAs to fill the machine: k * nchunks >= 2 * SMs when the window allows
+        size_t want = std::max<size_t>(1, (2 * (size_t)s->num_sms + s->k - 1) / s->k);
+        size_t c2 = std::max<size_t>(256, (win + want - 1) / want);
+        chunk = std::min(chunk, c2);
+        s->lag_chunk = (int)chunk;
+        s->lag_nchunks = (int)std::max<size_t>(1, (win + chunk - 1) / chunk);
+        const size_t L1 = s->L + 1, npairs = L1 * (L1 + 1) / 2;
+        if (dev_alloc(&s->lag_partial, (size_t)s->k * s->lag_nchunks * npairs)) return 1;
+    }
+    if (!s->missing) {
+        const size_t kk = (size_t)s->k * s->k;
+        if (dev_alloc(&s->YH, tk) || dev_alloc(&s->HTH, kk) || dev_alloc(&s->WTW, kk) ||
+            dev_alloc(&s->YtW, s->n * (size_t)s->k))
+            return 1;
+        if (s->sparse_storage && dev_alloc(&s->tmp_nk, s->n * (size_t)s->k)) return 1;
+        // split-K scratch: sized for the largest product (see gemm())
+        s->Cpart_elems = std::max(tk, s->n * (size_t)s->k) * 64 + kk * 1024;
+        size_t cap = ((size_t)1 << 31) / sizeof(double);   // never more than 2 GB
+        s->Cpart_elems = std::min(s->Cpart_elems, std::max(cap, std::max(tk, s->n * (size_t)s->k)));
+        if (dev_alloc(&s->Cpart, s->Cpart_elems)) return 1;
+    }
+    CUDA_TRY(cudaEventCreate(&s->ev0));
+    CUDA_TRY(cudaEventCreate(&s->ev1));
+    CUDA_TRY(cudaEventCreate(&s->ev2));
+    CUDA_TRY(cudaEventCreate(&s->ev3));
+    return 0;
+}
+
+static int check_lags(S *s, const uint32_t *lag_set, uint32_t lag_size) {
+    if (lag_set == nullptr || lag_size == 0) return fail("lag_set must be a non-empty sorted uint32 array");
+    if (lag_size > TRMF_MAX_LAGS) return fail("lag_set larger than %d is not supported", TRMF_MAX_LAGS);
+    s->lags.assign(lag_set, lag_set + lag_size);
+    s->L = (int)lag_size;
+    s->mid = (int)s->lags.back();   // trmf.cpp:79 -- "supposed to be the max index in lag_set"
+    for (uint32_t l : s->lags)
+        if ((int)l > s->mid) return fail("lag_set must be sorted ascending (last element is taken as the max lag)");
+    return 0;
+}
+
+extern "C" void trmf_b200_destroy(S *s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->own_Y) {
+        cudaFree(s->row_ptr); cudaFree(s->col_ptr); cudaFree(s->col_idx); cudaFree(s->row_idx);
+        cudaFree(s->val_t); cudaFree(s->val); cudaFree(s->Yd);
+    }
+    if (s->own_factors) { cudaFree(s->W); cudaFree(s->H); cudaFree(s->th); }
+    cudaFree(s->lags_dev);
+    cudaFree(s->g); cudaFree(s->s); cudaFree(s->r); cudaFree(s->d); cudaFree(s->Hd); cudaFree(s->wnew);
+    cudaFree(s->rho); cudaFree(s->scal); cudaFree(s->part); cudaFree(s->ticket);
+    cudaFree(s->YH); cudaFree(s->tmp_nk); cudaFree(s->HTH); cudaFree(s->WTW); cudaFree(s->YtW); cudaFree(s->Cpart);
+    cudaFree(s->lag_partial);
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev2) cudaEventDestroy(s->ev2);
+    if (s->ev3) cudaEventDestroy(s->ev3);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+template <typename T>
+static int h2d_new(S *s, T **dst, const void *src, size_t count) {
+    if (dev_alloc(dst, count)) return 1;
+    if (count) CUDA_TRY(cudaMemcpyAsync(*dst, src, count * sizeof(T), cudaMemcpyHostToDevice, s->stream));
+    return 0;
+}
+
+static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size,
+                            const PyMatrix *W, const PyMatrix *H, const PyMatrix *lag_val, int missing, int device) {
+    g_last_error.clear();
+    s->device = device;
+    s->T = Y->rows;
+    s->n = Y->cols;
+    s->k = (int)W->cols;
+    s->missing = missing != 0;
+    if (s->k < 1 || s->k > 128) return fail("rank k = %d outside the supported range 1..128", s->k);
+    if (check_lags(s, lag_set, lag_size)) return 1;
+    if (Y->type == TRMF_SPARSE) {
+        s->sparse_storage = true;
+        s->nnz = Y->nnz;
+    } else if (Y->type == TRMF_DENSE_ROWMAJOR || Y->type == TRMF_DENSE_COLMAJOR) {
+        if (s->missing) return fail("missing != 0 requires a sparse Y (the reference asserts in get_sparse(), trmf.cpp:229)");
+        s->sparse_storage = false;
+        s->dense_type = Y->type;
+        s->nnz = s->T * s->n;
+    } else {
+        return fail("unsupported PyMatrix type %d for Y", Y->type);
+    }
+    if (session_common_init(s)) return 1;
+    s->own_Y = true;
+    if (s->sparse_storage) {
+        if (h2d_new(s, &s->row_ptr, Y->row_ptr, s->T + 1) || h2d_new(s, &s->col_idx, Y->col_idx, s->nnz) ||
+            h2d_new(s, &s->val_t, Y->val_t, s->nnz) || h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) ||
+            h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) || h2d_new(s, &s->val, Y->val, s->nnz))
+            return 1;
+    } else {
+        if (h2d_new(s, &s->Yd, Y->val, s->T * s->n)) return 1;
+    }
+    s->own_factors = true;
+    if (h2d_new(s, &s->W, W->val, s->T * (size_t)s->k) || h2d_new(s, &s->H, H->val, s->n * (size_t)s->k) ||
+        h2d_new(s, &s->th, lag_val->val, (size_t)s->L * s->k))
+        return 1;
+    return 0;
+}
+
+extern "C" S *trmf_b200_create(const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size, const PyMatrix *W,
+                               const PyMatrix *H, const PyMatrix *lag_val, int32_t missing, int32_t device) {
+    S *s = new S();
+    if (create_host_impl(s, Y, lag_set, lag_size, W, H, lag_val, missing, device)) {
+        std::string keep = g_last_error;
+        trmf_b200_destroy(s);
+        g_last_error = keep;
+        return nullptr;
+    }
+    return s;
+}
+
+extern "C" S *trmf_b200_create_device(uint64_t T, uint64_t n, uint64_t nnz, uint32_t k, const uint64_t *d_row_ptr,
+                                      const uint32_t *d_col_idx, const void *d_val_t, const uint64_t *d_col_ptr,
+                                      const uint32_t *d_row_idx, const void *d_val, const uint32_t *lag_set_host,
+                                      uint32_t lag_size, void *d_W, void *d_H, void *d_lag_val, int32_t device) {
+    g_last_error.clear();
+    S *s = new S();
+    s->device = device;
+    s->T = T; s->n = n; s->nnz = nnz; s->k = (int)k;
+    s->missing = true;
+    s->sparse_storage = true;
+    int rc = 0;
+    if (k < 1 || k > 128) rc = fail("rank k = %u outside the supported range 1..128", k);
+    if (!rc) rc = check_lags(s, lag_set_host, lag_size);
+    if (!rc) rc = session_common_init(s);
+    if (rc) {
+        std::string keep = g_last_error;
+        trmf_b200_destroy(s);
+        g_last_error = keep;
+        return nullptr;
+    }
+    s->row_ptr = const_cast<uint64_t *>(d_row_ptr); s->col_idx = const_cast<uint32_t *>(d_col_idx);
+    s->val_t = (V *)const_cast<void *>(d_val_t);
+    s->col_ptr = const_cast<uint64_t *>(d_col_ptr); s->row_idx = const_cast<uint32_t *>(d_row_idx);
+    s->val = (V *)const_cast<void *>(d_val);
+    s->W = (V *)d_W; s->H = (V *)d_H; s->th = (V *)d_lag_val;
+    return s;
+}
+
+extern "C" int trmf_b200_set_params(S *s, double lambdaI, double lambdaAR, double lambdaLag) {
+    s->lambdaI = lambdaI; s->lambdaAR = lambdaAR; s->lambdaLag = lambdaLag;
+    return 0;
+}
+
+extern "C" int trmf_b200_set_stream(S *s, void *cuda_stream) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+    s->stream = (cudaStream_t)cuda_stream;
+    return 0;
+}
+
+extern "C" int trmf_b200_enable_timing(S *s, int32_t on) { s->timing = on != 0; return 0; }
+extern "C" int trmf_b200_sync(S *s) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+static int read_scalars(S *s) {
+    CUDA_TRY(cudaMemcpyAsync(s->h_scal, s->scal, SC_COUNT * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// --------------------------------------------------------------------------
+// building blocks
+// --------------------------------------------------------------------------
+static int dot(S *s, const V *a, const V *b, size_t n, int slot) {
+    LAUNCH(s, dot_kernel, ew_grid(s, n), 256, 0, a, b, n, s->part, s->ticket, s->scal + slot);
+    return 0;
+}
+
+// C (M x N, fp64 or V) = alpha * A(M x K, strided) * B (K x N row-major) + beta*addend [+ diag*I]
+template <typename TA, typename TB, typename TO>
+static int gemm(S *s, const TA *A, size_t sm, size_t sk, const TB *B, size_t M, int N, size_t K, double alpha,
+                const V *addend, double beta, double diag, TO *out) {
+    const size_t mt = (M + GT_M - 1) / GT_M;
+    size_t splits = std::max<size_t>(1, (2 * (size_t)s->num_sms + mt - 1) / mt);
+    splits = std::min(splits, std::max<size_t>(1, K / (GT_K * 2)));
+    splits = std::min(splits, std::max<size_t>(1, s->Cpart_elems / (M * (size_t)N)));
+    size_t kchunk = (K + splits - 1) / splits;
+    kchunk = (kchunk + GT_K - 1) / GT_K * GT_K;
+    splits = (K + kchunk - 1) / kchunk;
+    if (M * (size_t)N * splits > s->Cpart_elems) return fail("internal: split-K scratch too small");
+    dim3 grid((unsigned)mt, (unsigned)splits);
+    LAUNCH(s, (gemm_partial_kernel<TA, TB>), grid, 256, GT_K * N * sizeof(double), A, sm, sk, B, M, N, K, kchunk, s->Cpart);
+    LAUNCH(s, (gemm_finish_kernel<TO>), ew_grid(s, M * (size_t)N), 256, 0, s->Cpart, (int)splits, M * (size_t)N, N, alpha,
+           addend, beta, diag, out);
+    return 0;
+}
+
+template <int MODE>
+static int sparse_pass(S *s, const uint64_t *ptr, const uint32_t *col, const V *val, const V *Hm, const V *Sv, V *out,
+                       size_t rows, int fslot) {
+    const int k = s->k;
+    const int WARPS = 4;
+    const size_t smem = sparse_pass_smem(k, WARPS);
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((rows + WARPS - 1) / WARPS, (size_t)s->num_sms * 8));
+    double *fout = s->scal + (fslot >= 0 ? fslot : SC_TMP);
+#define SP_LAUNCH(KR)                                                                                         \
+    do {                                                                                                      \
+        CUDA_TRY(cudaFuncSetAttribute((sparse_pass_kernel<MODE, KR, WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LAUNCH(s, (sparse_pass_kernel<MODE, KR, WARPS>), grid, WARPS * 32, smem, ptr, col, val, Hm, Sv, out, k, rows, 0u, \
+               s->part, s->ticket, fout);                                                                     \
+    } while (0)
+    if (k <= 32) SP_LAUNCH(1);
+    else if (k <= 64) SP_LAUNCH(2);
+    else if (k <= 96) SP_LAUNCH(3);
+    else SP_LAUNCH(4);
+#undef SP_LAUNCH
+    return 0;
+}
+
+static LagSet lagset(const S *s) {
+    LagSet ls;
+    ls.L = s->L; ls.mid = s->mid; ls.lags = s->lags_dev;
+    return ls;
+}
+
+// arr_base_IX::grad / ::Hv : out = lI*v + lAR*A^T A v   (trmf.cpp:99-149)
+static int base_apply(S *s, const V *v, V *out) {
+    const size_t tk = s->T * (size_t)s->k;
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k);
+    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, out, s->T, s->k, s->lambdaI, s->lambdaAR);
+    return 0;
+}
+
+// dense-mode init(): YH = Y H, HTH = H^T H   (trmf.cpp:183-187)
+static int dense_loss_init(S *s) {
+    const int k = s->k;
+    if (s->sparse_storage) {
+        if (sparse_pass<MODE_SPMM>(s, s->row_ptr, s->col_idx, s->val_t, s->H, nullptr, s->YH, s->T, -1)) return 1;
+    } else {
+        const bool rm = s->dense_type == TRMF_DENSE_ROWMAJOR;
+        if (gemm<V, V, V>(s, s->Yd, rm ? s->n : 1, rm ? 1 : s->T, s->H, s->T, k, s->n, 1.0, nullptr, 0.0, 0.0, s->YH)) return 1;
+    }
+    if (gemm<V, V, double>(s, s->H, 1, (size_t)k, s->H, (size_t)k, k, s->n, 1.0, nullptr, 0.0, 0.0, s->HTH)) return 1;
+    // tr(Y^T Y)  (trmf.cpp:184)
+    if (s->sparse_storage) { if (dot(s, s->val_t, s->val_t, s->nnz, SC_TMP2)) return 1; }
+    else { if (dot(s, s->Yd, s->Yd, s->T * s->n, SC_TMP2)) return 1; }
+    return 0;
+}
+
+// objective value at v -> scal[slot]; dense-mode pieces are combined on the host after read_scalars()
+static int fun_launch(S *s, const V *v) {
+    const size_t tk = s->T * (size_t)s->k;
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k);
+    LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, v, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
+    if (s->missing) {
+        if (sparse_pass<MODE_FUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, v, nullptr, s->T, SC_FLOSS)) return 1;
+    } else {
+        // 0.5 trYTY + 0.5 <W^T W, HTH> - <YH, W>    (trmf.cpp:189-197)
+        const int k = s->k;
+        if (gemm<V, V, double>(s, v, 1, (size_t)k, v, (size_t)k, k, s->T, 1.0, nullptr, 0.0, 0.0, s->WTW)) return 1;
+        LAUNCH(s, dotd_kernel, 1, 256, 0, s->WTW, s->HTH, (size_t)k * k, s->part, s->ticket, s->scal + SC_TMP);
+        if (dot(s, s->YH, v, tk, SC_FLOSS)) return 1;
+    }
+    return 0;
+}
+static double fun_combine(const S *s) {
+    const double *h = s->h_scal;
+    if (s->missing) return h[SC_FLOSS] + h[SC_FBASE];
+    return h[SC_FBASE] + 0.5 * h[SC_TMP2] + 0.5 * h[SC_TMP] - h[SC_FLOSS];
+}
+
+static int grad_launch(S *s, const V *w, V *g) {
+    if (base_apply(s, w, g)) return 1;
+    if (s->missing) return sparse_pass<MODE_GRAD>(s, s->row_ptr, s->col_idx, s->val_t, s->H, w, g, s->T, -1);
+    // G += -YH + W HTH   (trmf.cpp:204-206)
+    const size_t tk = s->T * (size_t)s->k;
+    LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, g, -1.0, s->YH, 0.0, (const V *)nullptr, g, tk);
+    return gemm<V, double, V>(s, w, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, g, 1.0, 0.0, g);
+}
+
+static int hv_launch(S *s, const V *d, V *Hd) {
+    if (base_apply(s, d, Hd)) return 1;
+    if (s->missing) return sparse_pass<MODE_HV>(s, s->row_ptr, s->col_idx, s->val_t, s->H, d, Hd, s->T, -1);
+    return gemm<V, double, V>(s, d, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, Hd, 1.0, 0.0, Hd);
+}
+
+// --------------------------------------------------------------------------
+// the three phases
+// --------------------------------------------------------------------------
+extern "C" int trmf_b200_f_update(S *s) {
+    g_last_error.clear();
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    const int k = s->k;
+    if (s->missing) {
+        if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
+        if (f_update_tiled_supported(k)) {
+            if (f_update_tiled_launch(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, k, s->lambdaI,
+                                      (uint32_t)s->n, &s->launches))
+                return fail("f_update_tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else {
+            const int ENT = 32;
+            const size_t smem = f_update_generic_smem(k, ENT);
+            const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(s->n, (size_t)s->num_sms * 4));
+#define FG_LAUNCH(MAXP)                                                                                        \
+    do {                                                                                                       \
+        CUDA_TRY(cudaFuncSetAttribute((f_update_generic_kernel<MAXP, 256, ENT>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        LAUNCH(s, (f_update_generic_kernel<MAXP, 256, ENT>), grid, 256, smem, s->col_ptr, s->row_idx, s->val, s->W, s->H, k, \
+               s->lambdaI, (uint32_t)s->n);                                                                    \
+    } while (0)
+            if (k <= 40) FG_LAUNCH(4);
+            else if (k <= 64) FG_LAUNCH(9);
+            else FG_LAUNCH(33);
+#undef FG_LAUNCH
+        }
+        if (s->timing) CUDA_TRY(cudaEventRecord(s->ev3, s->stream));
+    } else {
+        // dense mode: YtW = Y^T W, G = W^T W + lI I, one factorisation, n solves (trmf.cpp:319-337)
+        if (s->sparse_storage) {
+            if (sparse_pass<MODE_SPMM>(s, s->col_ptr, s->row_idx, s->val, s->W, nullptr, s->tmp_nk, s->n, -1)) return 1;
+            // widen to fp64 for the solve
+            LAUNCH(s, (gemm_finish_kernel<double>), ew_grid(s, s->n * (size_t)k), 256, 0, (const double *)nullptr, 0,
+                   s->n * (size_t)k, k, 0.0, s->tmp_nk, 1.0, 0.0, s->YtW);
+        } else {
+            const bool rm = s->dense_type == TRMF_DENSE_ROWMAJOR;
+            if (gemm<V, V, double>(s, s->Yd, rm ? 1 : s->T, rm ? s->n : 1, s->W, s->n, k, s->T, 1.0, nullptr, 0.0, 0.0, s->YtW)) return 1;
+        }
+        if (gemm<V, V, double>(s, s->W, 1, (size_t)k, s->W, (size_t)k, k, s->T, 1.0, nullptr, 0.0, s->lambdaI, s->WTW)) return 1;
+        const size_t smem = sizeof(double) * ((size_t)(k + 1) * (k + 1) + k);
+        CUDA_TRY(cudaFuncSetAttribute(dense_f_solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LAUNCH(s, dense_f_solve_kernel<128>, (unsigned)((s->n + 255) / 256), 256, smem, s->WTW, s->YtW, s->n, k, s->H);
+    }
+    if (s->timing) {
+        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->ms_f = ms;
+        if (s->missing) { CUDA_TRY(cudaEventElapsedTime(&ms, s->ev2, s->ev3)); s->ms_fk = ms; }
+    }
+    return 0;
+}
+
+// One TRON step with pure CG: rf_tron.h:135-254 (max_iter = 1) + trcg 412-505.
+// Solver constants: eps_cg = 0.1, CG cap = max_cg_iter*max_tron_iter = 20
+// (trmf.h:90-93, trmf.cpp:603-606), clamped to the number of variables
+// (trmf.cpp:523-526); eta0 = 1e-4 (rf_tron.h:138).
+extern "C" int trmf_b200_x_update(S *s) {
+    g_last_error.clear();
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    const size_t tk = s->T * (size_t)s->k;
+    const unsigned eg = ew_grid(s, tk);
+    const double eps_cg = 0.1, eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
+    const size_t max_cg = std::min<size_t>(20, tk);
+
+    if (!s->missing && dense_loss_init(s)) return 1;   // fun_obj->init(), trmf.h:166-173
+    if (fun_launch(s, s->W)) return 1;
+    if (read_scalars(s)) return 1;                     // (the grad below does not depend on it; cheap)
+    const double f = fun_combine(s);
+    if (grad_launch(s, s->W, s->g)) return 1;
+    int cur = SC_RTR, nxt = SC_RNEW;
+    LAUNCH(s, cg_init_kernel, eg, 256, 0, s->g, s->s, s->r, s->d, tk, s->part, s->ticket, s->scal + cur);
+    if (read_scalars(s)) return 1;
+    const double gg = s->h_scal[cur];
+    const double gnorm = std::sqrt(gg);
+    s->st_f = f; s->st_fnew = f; s->st_gnorm = gnorm; s->st_cg = 0; s->st_acc = 0; s->st_prered = 0; s->st_actred = 0;
+    double delta = gnorm;
+    if (gnorm > 0.0) {   // rf_tron.h:170: `gnorm <= eps*gnorm1` can only hold for gnorm == 0
+        const double cgtol = eps_cg * gnorm;
+        double rTr = gg;
+        size_t cg_iter = 0;
+        double rnorm = gnorm;
+        while (true) {
+            rnorm = std::sqrt(rTr);
+            if (rnorm <= cgtol) break;
+            if (cg_iter >= max_cg) break;
+            ++cg_iter;
+            if (hv_launch(s, s->d, s->Hd)) return 1;
+            if (dot(s, s->d, s->Hd, tk, SC_DHD)) return 1;
+            LAUNCH(s, cg_step1_kernel, eg, 256, 0, s->s, s->r, s->d, s->Hd, tk, s->scal, cur, nxt, s->part, s->ticket);
+            LAUNCH(s, cg_step2_kernel, eg, 256, 0, s->d, s->r, tk, s->scal, cur, nxt);
+            if (read_scalars(s)) return 1;
+            rTr = s->h_scal[nxt];
+            std::swap(cur, nxt);
+        }
+        // trial point and the acceptance test (rf_tron.h:183-236)
+        LAUNCH(s, tron_trial_kernel, eg, 256, 0, s->W, s->s, s->g, s->r, s->wnew, tk, s->part, s->ticket,
+               s->scal + SC_GS, s->scal + SC_SR);
+        if (dot(s, s->s, s->s, tk, SC_DHD)) return 1;   // |s|^2, only feeds the (inert) trust radius / verbose line
+        if (read_scalars(s)) return 1;
+        const double gs = s->h_scal[SC_GS], sr = s->h_scal[SC_SR], snorm = std::sqrt(s->h_scal[SC_DHD]);
+        const double prered = -0.5 * (gs - sr);
+        if (fun_launch(s, s->wnew)) return 1;
+        if (read_scalars(s)) return 1;
+        const double fnew = fun_combine(s);
+        const double actred = f - fnew;
+        // trust-radius bookkeeping (rf_tron.h:196-217); inert under pure_cg but printed at verbose >= 2
+        delta = std::min(delta, snorm);
+        double alpha;
+        if (fnew - f - gs <= 0) alpha = sigma3;
+        else alpha = std::max(sigma1, -0.5 * (gs / (fnew - f - gs)));
+        if (actred < eta0 * prered) delta = std::min(std::max(alpha, sigma1) * snorm, sigma2 * delta);
+        else if (actred < eta1 * prered) delta = std::max(sigma1 * delta, std::min(alpha * snorm, sigma2 * delta));
+        else if (actred < eta2 * prered) delta = std::max(sigma1 * delta, std::min(alpha * snorm, sigma3 * delta));
+        else delta = std::max(delta, std::min(alpha * snorm, sigma3 * delta));
+        s->st_cg = (double)cg_iter; s->st_fnew = fnew; s->st_prered = prered; s->st_actred = actred;
+        s->st_delta = delta; s->st_rnorm = rnorm;
+        if (actred > eta0 * prered) {
+            s->st_acc = 1;
+            CUDA_TRY(cudaMemcpyAsync(s->W, s->wnew, tk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+            // (the reference recomputes the gradient here, rf_tron.h:229; its value is never used
+            //  because max_iter == 1 ends the loop -- not reproduced)
+        }
+    }
+    if (s->timing) {
+        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->ms_x = ms;
+    }
+    return 0;
+}
+
+extern "C" int trmf_b200_lag_update(S *s) {
+    g_last_error.clear();
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    const size_t smem1 = sizeof(double) * ((size_t)s->lag_chunk + s->mid);
+    CUDA_TRY(cudaFuncSetAttribute(lag_gram_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1));
+    dim3 grid((unsigned)s->k, (unsigned)s->lag_nchunks);
+    LAUNCH(s, lag_gram_kernel<256>, grid, 256, smem1, s->W, lagset(s), s->T, s->k, s->lag_chunk, s->lag_nchunks, s->lag_partial);
+    const size_t smem2 = sizeof(double) * ((size_t)(s->L + 1) * (s->L + 1) + s->L);
+    CUDA_TRY(cudaFuncSetAttribute(lag_solve_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+    LAUNCH(s, lag_solve_kernel<128>, (unsigned)s->k, 128, smem2, s->lag_partial, s->L, s->lag_nchunks, s->lambdaLag, s->th);
+    if (s->timing) {
+        CUDA_TRY(cudaEventRecord(s->ev1, s->stream));
+        CUDA_TRY(cudaEventSynchronize(s->ev1));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        s->ms_lag = ms;
+    }
+    return 0;
+}
+
+static int sq_norm(S *s, const V *a, size_t n, double *out) {
+    if (dot(s, a, a, n, SC_TMP)) return 1;
+    if (read_scalars(s)) return 1;
+    *out = s->h_scal[SC_TMP];
+    return 0;
+}
+
+// trmf_train's loop, trmf.cpp:647-693 (verbose trace formats 660-688, rf_tron.h:219)
+extern "C" int trmf_b200_train(S *s, int32_t max_iter, int32_t period_W, int32_t period_H, int32_t period_Lag, int32_t verbose) {
+    if (period_W <= 0 || period_H <= 0 || period_Lag <= 0) return fail("periods must be positive");
+    const size_t tk = s->T * (size_t)s->k, nk = s->n * (size_t)s->k, lk = (size_t)s->L * s->k;
+    for (int iter = 1; iter <= max_iter; ++iter) {
+        double nv = 0;
+        if (iter % period_H == 0) {
+            if (trmf_b200_f_update(s)) return 1;
+            if (verbose) { if (sq_norm(s, s->H, nk, &nv)) return 1; fprintf(stderr, ">> iter %d F %g\n", iter, nv); }
+        }
+        if (iter % period_W == 0) {
+            if (trmf_b200_x_update(s)) return 1;
+            if (verbose >= 2) {
+                fprintf(stdout, "iter %2d act %5.3e pre %5.3e delta %5.3e f %5.3e |g| %5.3e CG %3d |g| %5.3e\n", 1, s->st_actred,
+                        s->st_prered, s->st_delta, s->st_f, s->st_gnorm, (int)s->st_cg, s->st_rnorm);
+                fflush(stdout);
+            }
+            if (verbose) { if (sq_norm(s, s->W, tk, &nv)) return 1; fprintf(stderr, ">> iter %d X %g\n", iter, nv); }
+        }
+        if (iter % period_Lag == 0) {
+            if (verbose) { if (sq_norm(s, s->th, lk, &nv)) return 1; fprintf(stderr, ">> iter %d LV(%d %d) %g\n", iter, s->L, s->k, nv); }
+            if (trmf_b200_lag_update(s)) return 1;
+            if (verbose) { if (sq_norm(s, s->th, lk, &nv)) return 1; fprintf(stderr, ">> iter %d LV %g\n", iter, nv); }
+        }
+    }
+    return 0;
+}
+
+extern "C" int trmf_b200_download(S *s, void *W, void *H, void *lag_val) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (W) CUDA_TRY(cudaMemcpyAsync(W, s->W, s->T * (size_t)s->k * sizeof(V), cudaMemcpyDeviceToHost, s->stream));
+    if (H) CUDA_TRY(cudaMemcpyAsync(H, s->H, s->n * (size_t)s->k * sizeof(V), cudaMemcpyDeviceToHost, s->stream));
+    if (lag_val) CUDA_TRY(cudaMemcpyAsync(lag_val, s->th, (size_t)s->L * s->k * sizeof(V), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" int trmf_b200_upload(S *s, const void *W, const void *H, const void *lag_val) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (W) CUDA_TRY(cudaMemcpyAsync(s->W, W, s->T * (size_t)s->k * sizeof(V), cudaMemcpyHostToDevice, s->stream));
+    if (H) CUDA_TRY(cudaMemcpyAsync(s->H, H, s->n * (size_t)s->k * sizeof(V), cudaMemcpyHostToDevice, s->stream));
+    if (lag_val) CUDA_TRY(cudaMemcpyAsync(s->th, lag_val, (size_t)s->L * s->k * sizeof(V), cudaMemcpyHostToDevice, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+extern "C" double trmf_b200_stat(S *s, int32_t which) {
+    switch (which) {
+        case TRMF_STAT_CG_ITERS: return s->st_cg;
+        case TRMF_STAT_ACCEPTED: return s->st_acc;
+        case TRMF_STAT_F: return s->st_f;
+        case TRMF_STAT_FNEW: return s->st_fnew;
+        case TRMF_STAT_GNORM: return s->st_gnorm;
+        case TRMF_STAT_KERNEL_LAUNCHES: return (double)s->launches;
+        case TRMF_STAT_F_MS: return s->ms_f;
+        case TRMF_STAT_X_MS: return s->ms_x;
+        case TRMF_STAT_LAG_MS: return s->ms_lag;
+        case TRMF_STAT_F_KERNEL_MS: return s->ms_fk;
+        case TRMF_STAT_PRERED: return s->st_prered;
+        case TRMF_STAT_ACTRED: return s->st_actred;
+    }
+    return NAN;
+}
+
+// --------------------------------------------------------------------------
+// library info
+// --------------------------------------------------------------------------
+extern "C" int trmf_b200_value_bytes(void) { return (int)sizeof(V); }
+extern "C" const char *trmf_b200_version(void) { return TRMF_B200_VERSION; }
+extern "C" const char *trmf_b200_last_error(void) { return g_last_error.c_str(); }
+extern "C" int trmf_b200_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+// --------------------------------------------------------------------------
+// the drop-in entry point
+// --------------------------------------------------------------------------
+static bool is_rowmajor(const PyMatrix *m) { return m->type == TRMF_DENSE_ROWMAJOR; }
+static bool is_colmajor(const PyMatrix *m) { return m->type == TRMF_DENSE_COLMAJOR; }
+
+// check_dimension, trmf.cpp:561-596 -- same messages, same "print and return" behaviour
+static bool check_dimension(const PyMatrix *Y, uint32_t lag_size, const PyMatrix *W, const PyMatrix *H, const PyMatrix *lv) {
+    bool pass = true;
+    if (Y->rows != W->rows) { fprintf(stderr, "[ERR MSG]: Y.rows (%ld) != W.rows (%ld)\n", (long)Y->rows, (long)W->rows); pass = false; }
+    if (Y->cols != H->rows) { fprintf(stderr, "[ERR MSG]: Y.cols (%ld) != H.rows (%ld)\n", (long)Y->cols, (long)H->rows); pass = false; }
+    if (W->cols != H->cols) { fprintf(stderr, "[ERR MSG]: W.cols (%ld) != H.cols (%ld)\n", (long)W->cols, (long)H->cols); pass = false; }
+    if (lag_size != lv->rows) { fprintf(stderr, "[ERR MSG]: lag_set.size(%ld) != lag_val.rows(%ld)\n", (long)lag_size, (long)lv->rows); pass = false; }
+    if (W->cols != lv->cols) { fprintf(stderr, "[ERR MSG]: W.cols(%ld) != lag_val.cols(%ld)\n", (long)W->cols, (long)lv->cols); pass = false; }
+    if (!is_rowmajor(W)) { fprintf(stderr, "[ERR MSG]: W should be rowmajored\n"); pass = false; }
+    if (!is_rowmajor(H)) { fprintf(stderr, "[ERR MSG]: H should be rowmajored\n"); pass = false; }
+    if (!is_colmajor(lv)) { fprintf(stderr, "[ERR MSG]: lag_val should be colmajored\n"); pass = false; }
+    fflush(stderr);
+    return pass;
+}
+
+extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t py_lag_size, PyMatrix *pyW, PyMatrix *pyH,
+                             PyMatrix *pylag_val, int warm_start, double lambdaI, double lambdaAR, double lambdaLag,
+                             int32_t max_iter, int32_t period_W, int32_t period_H, int32_t period_Lag, int32_t threads,
+                             int32_t missing, int32_t verbose) {
+    g_last_error.clear();
+    const int solver_type = missing != 0 ? 31 : 30;
+    if (verbose > 0) {   // parameter dump, trmf.cpp:607-629 (max_tron_iter already merged: 603-606)
+        fprintf(stdout, ">> param.solver_type %d\n", solver_type);
+        fprintf(stdout, ">> param.max_iter %d\n", max_iter);
+        fprintf(stdout, ">> param.lambdaI %g\n", lambdaI);
+        fprintf(stdout, ">> param.lambdaAR %g\n", lambdaAR);
+        fprintf(stdout, ">> param.lambdaLag %g\n", lambdaLag);
+        fprintf(stdout, ">> param.period_W %d\n", period_W);
+        fprintf(stdout, ">> param.period_H %d\n", period_H);
+        fprintf(stdout, ">> param.period_Lag %d\n", period_Lag);
+        fprintf(stdout, ">> param.threads %d\n", threads);
+        fprintf(stdout, ">> param.verbose %d\n", verbose);
+        fprintf(stdout, ">> param.eps %g\n", 0.1);
+        fprintf(stdout, ">> param.eps_cg %g\n", 0.1);
+        fprintf(stdout, ">> param.max_tron_iter %d\n", 1);
+        fprintf(stdout, ">> param.max_cg_iter %d\n", 20);
+        fprintf(stdout, ">> prob.lag_size %ld:  ", (long)py_lag_size);
+        for (uint32_t i = 0; i < py_lag_size; ++i) fprintf(stdout, " %d", (int)py_lag_set[i]);
+        fprintf(stdout, "\n");
+        fflush(stdout);
+    }
+    if (!warm_start) {
+        // trmf_initialization, trmf.cpp:547-559: W,H ~ U(0,1), lag_val ~ N(0,1) from a default-seeded
+        // Mersenne twister.  (Never reached from Python: trmf.py:259 always passes warm_start=True.)
+        std::mt19937 rng;
+        std::uniform_real_distribution<double> U(0.0, 1.0);
+        std::normal_distribution<double> N(0.0, 1.0);
+        V *w = (V *)pyW->val, *h = (V *)pyH->val, *lv = (V *)pylag_val->val;
+        for (size_t i = 0; i < pyW->rows * pyW->cols; ++i) w[i] = (V)U(rng);
+        for (size_t i = 0; i < pyH->rows * pyH->cols; ++i) h[i] = (V)U(rng);
+        for (size_t i = 0; i < pylag_val->rows * pylag_val->cols; ++i) lv[i] = (V)N(rng);
+        pyW->type = TRMF_DENSE_ROWMAJOR; pyH->type = TRMF_DENSE_ROWMAJOR; pylag_val->type = TRMF_DENSE_COLMAJOR;
+    }
+    if (!check_dimension(pyY, py_lag_size, pyW, pyH, pylag_val)) return;
+    (void)threads;   // OpenMP thread count of the reference (trmf.cpp:636): no meaning here
+    S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, 0);
+    if (!s) return;   // message already on stderr
+    trmf_b200_set_params(s, lambdaI, lambdaAR, lambdaLag);
+    if (trmf_b200_train(s, max_iter, period_W, period_H, period_Lag, verbose) == 0)
+        trmf_b200_download(s, pyW->val, pyH->val, pylag_val->val);
+    std::string keep = g_last_error;
+    trmf_b200_destroy(s);
+    g_last_error = keep;
+}
+
+#include "extras.cuh"   // multi-GPU (NCCL) and on-device synthetic data

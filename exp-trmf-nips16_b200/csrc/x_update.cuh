@@ -1,0 +1,271 @@
+// x_update.cuh -- K2..K6: the AR-regularised update of the temporal factor ("X rows").
+//
+// The reference takes ONE inexact Newton step per outer iteration
+// (arr_solver::solve trmf.h:175-186 -> TRON::tron_trustregion rf_tron.h:135-254
+// with max_iter = 1, pure CG trcg rf_tron.h:412-505, <= 20 steps, stop when
+// ||r|| <= 0.1 ||g||, accept iff actred > 1e-4 prered).  The objective pieces:
+//   arr_base_IX   (trmf.cpp:70-149)   0.5 lI |W|^2 + 0.5 lAR sum_{i>=m} |rho_i|^2
+//   arr_ls_pY_IX  (trmf.cpp:231-288)  0.5 sum_Omega (Y_ij - <W_i,H_j>)^2
+// Kernels below evaluate fun / grad / Hv of these on the device.  Layouts:
+// W,S,G,... are T x k row-major; H is n x k row-major; Theta (lag_val) is
+// L x k column-major (Theta(l,t) = th[L*t + l]); Y is CSR by time stamp.
+#pragma once
+#include "common.cuh"
+
+#define TRMF_MAX_LAGS 512
+
+struct LagSet {           // passed by value (kernel parameter space)
+    int L;
+    int mid;              // max lag = last element of the sorted set (trmf.cpp:79)
+    const uint32_t *lags; // device
+};
+
+// rho[i,t] = S[i,t] - sum_l Theta[l,t] S[i-lag_l,t]   (i >= mid), 0 otherwise.
+// Residual in fp64 exactly like the reference (trmf.cpp:110-114).  One thread
+// per (i,t), t fastest => coalesced over the row-major T x k layout.
+__global__ void ar_rho_kernel(const V *__restrict__ S, const V *__restrict__ th, LagSet ls,
+                              double *__restrict__ rho, size_t T, int k) {
+    const size_t total = T * (size_t)k;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t i = p / k;
+        const int t = (int)(p - i * k);
+        double r = 0.0;
+        if (i >= (size_t)ls.mid) {
+            r = (double)S[p];
+            const V *tht = th + (size_t)ls.L * t;
+            for (int l = 0; l < ls.L; ++l) r -= (double)tht[l] * (double)S[p - (size_t)ls.lags[l] * k];
+        }
+        rho[p] = r;
+    }
+}
+
+// out[j,t] = lI * S[j,t] + lAR * ( rho[j,t] - sum_l Theta[l,t] rho[j+lag_l,t] )
+// = the closed form of the reference's forward-residual / adjoint-scatter loop
+// (trmf.cpp:102-121 grad, 128-147 Hv).  Terms with j+lag_l >= T are dropped;
+// rho is stored as 0 below mid.
+__global__ void ar_apply_kernel(const V *__restrict__ S, const V *__restrict__ th, LagSet ls,
+                                const double *__restrict__ rho, V *__restrict__ out,
+                                size_t T, int k, double lambdaI, double lambdaAR) {
+    const size_t total = T * (size_t)k;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const size_t j = p / k;
+        const int t = (int)(p - j * k);
+        double a = rho[p];
+        const V *tht = th + (size_t)ls.L * t;
+        for (int l = 0; l < ls.L; ++l) {
+            const size_t jj = j + ls.lags[l];
+            if (jj < T) a -= (double)tht[l] * rho[jj * k + t];
+        }
+        out[p] = (V)(lambdaI * (double)S[p] + lambdaAR * a);
+    }
+}
+
+// scal[slot] = 0.5*lI*|S|^2 + 0.5*lAR*|rho|^2   (arr_base_IX::fun, trmf.cpp:70-97)
+__global__ void base_fun_kernel(const V *__restrict__ S, const double *__restrict__ rho, size_t total,
+                                double lambdaI, double lambdaAR, double *part, unsigned *ticket, double *out) {
+    __shared__ double red[32];
+    double a = 0.0, b = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const double s = (double)S[p], r = rho[p];
+        a += s * s;
+        b += r * r;
+    }
+    double v = 0.5 * lambdaI * a + 0.5 * lambdaAR * b;
+    v = block_sum(v, red);
+    grid_sum_commit(v, part, ticket, out, 1.0, red);
+}
+
+// ---------------------------------------------------------------------------
+// One pass over Omega (by-time CSR): one warp per time stamp i.
+//   MODE_FUN : out scalar += sum_j (Y_ij - <S_i,H_j>)^2      (trmf.cpp:231-245, fp64 sum)
+//   MODE_GRAD: out_i += sum_j (<S_i,H_j> - Y_ij) H_j          (trmf.cpp:247-267)
+//   MODE_HV  : out_i += sum_j  <S_i,H_j> H_j                  (trmf.cpp:269-288)
+//   MODE_SPMM: out_i  = sum_j  Y_ij H_j                       (smat_x_dmat, dense-mode YH with sparse storage)
+// 32 entries at a time: their H rows are gathered (coalesced along k) into a
+// per-warp shared tile with an odd row stride; phase A: lane e forms the dot
+// for entry e; phase B: lane t accumulates column t over the 32 entries.
+// fp32 build: fp32 FMAs within a 32-entry tile, fp64 across tiles.
+// ---------------------------------------------------------------------------
+enum { MODE_FUN = 0, MODE_GRAD = 1, MODE_HV = 2, MODE_SPMM = 3 };
+
+template <int MODE, int KR, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ col,
+                   const V *__restrict__ val, const V *__restrict__ H, const V *__restrict__ S,
+                   V *__restrict__ out, int k, size_t T, uint32_t col_base,
+                   double *part, unsigned *ticket, double *fout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int ks = k | 1;   // odd stride: conflict-free column walks
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    V *tile = reinterpret_cast<V *>(smem_raw) + (size_t)wid * (32 * ks + k);
+    V *svec = tile + 32 * ks;
+    __shared__ double red[32];
+    double fsum = 0.0;
+
+    for (size_t i = (size_t)blockIdx.x * WARPS + wid; i < T; i += (size_t)gridDim.x * WARPS) {
+        const uint64_t lo = ptr[i], hi = ptr[i + 1];
+        if (MODE != MODE_SPMM) {
+#pragma unroll
+            for (int q = 0; q < KR; ++q) { const int t = lane + 32 * q; if (t < k) svec[t] = S[i * k + t]; }
+        }
+        double accd[KR];
+#pragma unroll
+        for (int q = 0; q < KR; ++q) accd[q] = 0.0;
+        for (uint64_t base = lo; base < hi; base += 32) {
+            const uint64_t e = base + lane;
+            const bool valid = e < hi;
+            const uint32_t j = valid ? col[e] - col_base : 0u;
+            const V y = (valid && MODE != MODE_HV) ? val[e] : (V)0;
+            const int cnt = (int)((hi - base) < 32 ? (hi - base) : 32);
+            __syncwarp();
+            for (int r = 0; r < cnt; ++r) {
+                const uint32_t jr = __shfl_sync(FULL_MASK, j, r);
+#pragma unroll
+                for (int q = 0; q < KR; ++q) { const int t = lane + 32 * q; if (t < k) tile[r * ks + t] = H[(size_t)jr * k + t]; }
+            }
+            __syncwarp();
+            V z;
+            if (MODE == MODE_SPMM) {
+                z = y;
+            } else {
+                z = (V)0;
+                if (valid) {
+                    const V *hr = tile + lane * ks;
+                    for (int t = 0; t < k; ++t) z += svec[t] * hr[t];
+                }
+                if (MODE == MODE_GRAD) z -= y;
+                if (MODE == MODE_FUN) { const double rr = (double)y - (double)z; if (valid) fsum += rr * rr; }
+            }
+            if (MODE != MODE_FUN) {
+                V accf[KR];
+#pragma unroll
+                for (int q = 0; q < KR; ++q) accf[q] = (V)0;
+                for (int r = 0; r < cnt; ++r) {
+                    const V zr = __shfl_sync(FULL_MASK, z, r);
+#pragma unroll
+                    for (int q = 0; q < KR; ++q) { const int t = lane + 32 * q; if (t < k) accf[q] += zr * tile[r * ks + t]; }
+                }
+#pragma unroll
+                for (int q = 0; q < KR; ++q) accd[q] += (double)accf[q];
+            }
+        }
+        if (MODE != MODE_FUN) {
+#pragma unroll
+            for (int q = 0; q < KR; ++q) {
+                const int t = lane + 32 * q;
+                if (t < k) {
+                    if (MODE == MODE_SPMM) out[i * k + t] = (V)accd[q];
+                    else out[i * k + t] = (V)((double)out[i * k + t] + accd[q]);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    if (MODE == MODE_FUN) {
+        double v = block_sum(fsum, red);
+        grid_sum_commit(v, part, ticket, fout, 0.5, red);
+    }
+}
+
+static inline size_t sparse_pass_smem(int k, int warps) {
+    return sizeof(V) * (size_t)warps * (32 * (k | 1) + k);
+}
+
+// ---------------------------------------------------------------------------
+// CG / TRON vector algebra (rf_tron.h:424-502), fused, scalars resident in
+// device memory (double), reductions deterministic.
+// ---------------------------------------------------------------------------
+enum {   // slots of the device scalar block
+    SC_F = 0, SC_FBASE, SC_FLOSS, SC_FNEW, SC_GG, SC_RTR, SC_DHD, SC_RNEW, SC_GS, SC_SR, SC_TMP, SC_TMP2,
+    SC_COUNT = 16
+};
+
+// out[slot] = <a,b>
+__global__ void dot_kernel(const V *__restrict__ a, const V *__restrict__ b, size_t n,
+                           double *part, unsigned *ticket, double *out) {
+    __shared__ double red[32];
+    double v = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
+        v += (double)a[p] * (double)b[p];
+    v = block_sum(v, red);
+    grid_sum_commit(v, part, ticket, out, 1.0, red);
+}
+
+// s = 0, r = d = -g ; rTr = <g,g>         (rf_tron.h:424-436)
+__global__ void cg_init_kernel(const V *__restrict__ g, V *__restrict__ s, V *__restrict__ r, V *__restrict__ d,
+                               size_t n, double *part, unsigned *ticket, double *rtr) {
+    __shared__ double red[32];
+    double v = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const V gv = g[p];
+        s[p] = (V)0;
+        r[p] = -gv;
+        d[p] = -gv;
+        v += (double)gv * (double)gv;
+    }
+    v = block_sum(v, red);
+    grid_sum_commit(v, part, ticket, rtr, 1.0, red);
+}
+
+// alpha = rTr / dHd ; s += alpha d ; r -= alpha Hd ; rnew = <r,r>   (rf_tron.h:460-493)
+__global__ void cg_step1_kernel(V *__restrict__ s, V *__restrict__ r, const V *__restrict__ d, const V *__restrict__ Hd,
+                                size_t n, double *scal, int cur, int nxt, double *part, unsigned *ticket) {
+    __shared__ double red[32];
+    const double alpha = scal[cur] / scal[SC_DHD];
+    const V a = (V)alpha;
+    double v = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        s[p] = s[p] + a * d[p];
+        const V rv = r[p] - a * Hd[p];
+        r[p] = rv;
+        v += (double)rv * (double)rv;
+    }
+    v = block_sum(v, red);
+    grid_sum_commit(v, part, ticket, scal + nxt, 1.0, red);
+}
+
+// beta = rnew / rTr ; d += (beta-1) d ; d += r                      (rf_tron.h:494-502)
+// (rTr <- rnew is done by swapping the two scalar slots `cur`/`nxt` on the host)
+__global__ void cg_step2_kernel(V *__restrict__ d, const V *__restrict__ r, size_t n, const double *scal, int cur, int nxt) {
+    const double beta = scal[nxt] / scal[cur];
+    const V bm1 = (V)beta - (V)1;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        V dv = d[p];
+        dv = dv + bm1 * dv;
+        d[p] = dv + r[p];
+    }
+}
+
+// w_new = w + s ; gs = <g,s> ; sr = <s,r>                           (rf_tron.h:183-190)
+__global__ void tron_trial_kernel(const V *__restrict__ w, const V *__restrict__ s, const V *__restrict__ g,
+                                  const V *__restrict__ r, V *__restrict__ wnew, size_t n,
+                                  double *part, unsigned *ticket, double *gs_out, double *sr_out) {
+    __shared__ double red[32];
+    double a = 0.0, b = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const V sv = s[p];
+        wnew[p] = w[p] + sv;
+        a += (double)g[p] * (double)sv;
+        b += (double)sv * (double)r[p];
+    }
+    a = block_sum(a, red);
+    b = block_sum(b, red);
+    // two commits share the ticket: do them through two partial arrays
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        part[blockIdx.x] = a;
+        part[gridDim.x + blockIdx.x] = b;
+        __threadfence();
+        unsigned t = atomicAdd(ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double va = 0.0, vb = 0.0;
+        for (unsigned i = threadIdx.x; i < gridDim.x; i += blockDim.x) { va += __ldcg(part + i); vb += __ldcg(part + gridDim.x + i); }
+        va = block_sum(va, red);
+        vb = block_sum(vb, red);
+        if (threadIdx.x == 0) { *gs_out = va; *sr_out = vb; *ticket = 0u; }
+    }
+}

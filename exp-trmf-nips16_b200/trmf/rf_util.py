@@ -1,0 +1,132 @@
+"""ctypes boundary of the B200 TRMF solver: the ``PyMatrix`` struct and the
+library loader.
+
+Mirrors the *interface* of the reference's ``python/trmf/rf_util.py`` (the
+80-byte ``PyMatrix`` POD at rf_util.py:35-52 == rf_matrix.h:3399-3415, the
+twin CSR+CSC buffers with uint64 pointers / uint32 indices at rf_util.py:88-98,
+``load_dynamic_library`` at rf_util.py:19-32) on NumPy >= 2 / SciPy >= 1.14.
+
+The libraries loaded here are CUDA-only.  If they are missing they are built
+with nvcc (``make -C corelib lib``); if that fails, or no B200 is visible at
+call time, the failure is loud -- there is no CPU implementation to fall back
+to.
+"""
+import ctypes
+import glob
+import os
+import subprocess
+
+import numpy as np
+import scipy.sparse as sps
+
+__all__ = ["PyMatrix", "fillprototype", "load_dynamic_library"]
+
+
+def fillprototype(fn, restype, argtypes):
+    fn.restype = restype
+    fn.argtypes = argtypes
+
+
+def load_dynamic_library(dirname, soname, forced_rebuild=False):
+    """``glob(dirname/soname*.so)[0]`` -> CDLL, running ``make -C dirname lib``
+    first when asked to or when nothing is there (rf_util.py:19-32)."""
+    def find():
+        hits = sorted(glob.glob(os.path.join(dirname, soname) + "*.so"))
+        return hits[0] if hits else None
+
+    so = None if forced_rebuild else find()
+    if so is None:
+        proc = subprocess.run(["make", "-C", dirname, "lib"], capture_output=True, text=True)
+        so = find()
+        if so is None:
+            raise RuntimeError(
+                "{} CUDA library cannot be found and could not be built with nvcc:\n{}".format(
+                    soname, proc.stdout[-2000:] + proc.stderr[-2000:]))
+    return ctypes.CDLL(so)
+
+
+class PyMatrix(ctypes.Structure):
+    """Zero-copy view descriptor handed to ``c_trmf_train``.
+
+    sparse: ``row_ptr/col_idx/val_t`` is the CSR and ``col_ptr/row_idx/val`` the
+    CSC of the same matrix; dense: only ``val`` (row- or column-major, see
+    ``type``).  The NumPy arrays are kept alive in ``py_buf``; ``py_buf['val']``
+    of a dense matrix is the array the solver updates in place.
+    """
+    DENSE_ROWMAJOR = 1
+    DENSE_COLMAJOR = 2
+    SPARSE = 3
+    EYE = 4
+
+    _fields_ = [
+        ("rows", ctypes.c_uint64),
+        ("cols", ctypes.c_uint64),
+        ("nnz", ctypes.c_uint64),
+        ("row_ptr", ctypes.POINTER(ctypes.c_uint64)),
+        ("col_ptr", ctypes.POINTER(ctypes.c_uint64)),
+        ("row_idx", ctypes.POINTER(ctypes.c_uint32)),
+        ("col_idx", ctypes.POINTER(ctypes.c_uint32)),
+        ("val", ctypes.c_void_p),
+        ("val_t", ctypes.c_void_p),
+        ("type", ctypes.c_int32),
+    ]
+
+    def __init__(self, A, dtype=np.float32, major=None):
+        """``major`` ('row' / 'col', optional, additive to the reference signature)
+        settles the type tag of arrays that are both C- and F-contiguous (a
+        single row or column, e.g. W with k == 1), which the reference would tag
+        COLMAJOR and then reject for W/H."""
+        super().__init__()
+        if A is None:
+            return
+        dtype = np.dtype(dtype)
+        self.dtype = dtype
+        self.py_buf = buf = {}
+        self.rows, self.cols = int(A.shape[0]), int(A.shape[1])
+        if sps.issparse(A):
+            if A.format == "coo":
+                # explicit COO keeps duplicates apart in the reference (rf_util.py:100-119);
+                # here they are summed, which is what every caller in trmf.py relies on.
+                A = A.tocsr()
+            csr = sps.csr_matrix(A)
+            csc = sps.csc_matrix(A)
+            if not csr.has_sorted_indices:
+                csr = csr.sorted_indices()
+            if not csc.has_sorted_indices:
+                csc = csc.sorted_indices()
+            self.type = PyMatrix.SPARSE
+            self.nnz = int(csr.indptr[-1])
+            buf["row_ptr"] = csr.indptr.astype(np.uint64)
+            buf["col_idx"] = csr.indices.astype(np.uint32)
+            buf["val_t"] = csr.data.astype(dtype)
+            buf["col_ptr"] = csc.indptr.astype(np.uint64)
+            buf["row_idx"] = csc.indices.astype(np.uint32)
+            buf["val"] = csc.data.astype(dtype)
+        elif isinstance(A, np.ndarray):
+            arr = A.astype(dtype)   # order='K': keeps the caller's memory layout
+            if not (arr.flags.c_contiguous or arr.flags.f_contiguous):
+                arr = np.ascontiguousarray(arr)
+            buf["val"] = arr
+            # same precedence as the reference (rf_util.py:123-126): F-contiguous wins
+            self.type = PyMatrix.DENSE_COLMAJOR if arr.flags.f_contiguous else PyMatrix.DENSE_ROWMAJOR
+            if major is not None and arr.flags.c_contiguous and arr.flags.f_contiguous:
+                self.type = PyMatrix.DENSE_ROWMAJOR if major == "row" else PyMatrix.DENSE_COLMAJOR
+            self.nnz = self.rows * self.cols
+        else:
+            raise TypeError("PyMatrix expects a numpy.ndarray or a scipy.sparse matrix, got {}".format(type(A)))
+        fields = dict(PyMatrix._fields_)
+        for name, arr in buf.items():
+            ctype = fields[name]
+            if ctype is ctypes.c_void_p:
+                setattr(self, name, arr.ctypes.data)
+            else:
+                setattr(self, name, arr.ctypes.data_as(ctype))
+
+    @classmethod
+    def identity(cls, size, dtype=np.float32):
+        eye = cls(None)
+        eye.rows = eye.cols = eye.nnz = int(size)
+        eye.dtype = np.dtype(dtype)
+        eye.py_buf = {}
+        eye.type = PyMatrix.EYE
+        return eye

@@ -1,0 +1,167 @@
+"""Device-resident session API (additive; not part of the reference surface).
+
+Thin ctypes binding of the ``trmf_b200_*`` symbols of ``include/trmf_b200.h``:
+Y, the factors and all work vectors stay in HBM across phase calls.  Used by
+``bench.py`` (kernel-resident timing, multi-GPU) and by the per-phase parity
+tests; ``trmf.train`` itself goes through the drop-in ``c_trmf_train``.
+"""
+import ctypes
+from ctypes import POINTER, byref, c_double, c_int32, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+from .rf_util import PyMatrix
+from .trmf import _clib
+
+STAT = dict(cg_iters=0, accepted=1, f=2, fnew=3, gnorm=4, kernel_launches=5,
+            f_ms=6, x_ms=7, lag_ms=8, f_kernel_ms=9, prered=10, actred=11)
+
+
+class SynthDesc(ctypes.Structure):
+    _fields_ = [("T", c_uint64), ("n", c_uint64), ("nnz", c_uint64),
+                ("d_row_ptr", c_void_p), ("d_col_idx", c_void_p), ("d_val_t", c_void_p),
+                ("d_col_ptr", c_void_p), ("d_row_idx", c_void_p), ("d_val", c_void_p)]
+
+
+_proto_done = set()
+
+
+def _lib(dtype):
+    lib = _clib.pick(dtype)
+    if id(lib) in _proto_done:
+        return lib
+    P = POINTER(PyMatrix)
+    lib.trmf_b200_create.restype = c_void_p
+    lib.trmf_b200_create.argtypes = [P, POINTER(c_uint32), c_uint32, P, P, P, c_int32, c_int32]
+    lib.trmf_b200_create_device.restype = c_void_p
+    lib.trmf_b200_create_device.argtypes = [c_uint64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p,
+                                            c_void_p, c_void_p, c_void_p, POINTER(c_uint32), c_uint32,
+                                            c_void_p, c_void_p, c_void_p, c_int32]
+    lib.trmf_b200_destroy.restype = None
+    lib.trmf_b200_destroy.argtypes = [c_void_p]
+    lib.trmf_b200_set_params.argtypes = [c_void_p, c_double, c_double, c_double]
+    lib.trmf_b200_set_stream.argtypes = [c_void_p, c_void_p]
+    for name in ("f_update", "x_update", "lag_update", "sync"):
+        getattr(lib, "trmf_b200_" + name).argtypes = [c_void_p]
+    lib.trmf_b200_train.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]
+    lib.trmf_b200_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.trmf_b200_upload.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.trmf_b200_stat.restype = c_double
+    lib.trmf_b200_stat.argtypes = [c_void_p, c_int32]
+    lib.trmf_b200_enable_timing.argtypes = [c_void_p, c_int32]
+    lib.trmf_b200_nccl_unique_id.argtypes = [c_void_p]
+    lib.trmf_b200_dist_init.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
+    lib.trmf_b200_allgather_H.argtypes = [c_void_p, c_void_p, POINTER(c_uint64)]
+    lib.trmf_b200_synth_generate.argtypes = [POINTER(SynthDesc), c_uint64, c_uint64, c_uint64, c_uint64, c_uint32,
+                                             c_double, c_double, c_uint64, c_int32]
+    lib.trmf_b200_free_synth.restype = None
+    lib.trmf_b200_free_synth.argtypes = [POINTER(SynthDesc)]
+    lib.trmf_b200_version.restype = ctypes.c_char_p
+    lib.trmf_b200_value_bytes.restype = c_int32
+    _proto_done.add(id(lib))
+    return lib
+
+
+def _check(lib, rc, what):
+    if rc != 0:
+        raise RuntimeError("trmf (CUDA) {} failed: {}".format(what, lib.trmf_b200_last_error().decode()))
+
+
+class Session(object):
+    """``Session(Y, lag_set, W, H, lag_val, missing=True)`` uploads everything
+    once; ``f_update() / x_update() / lag_update() / train(...)`` run on the
+    device; ``download()`` returns (W, H, lag_val) as NumPy arrays."""
+
+    def __init__(self, Y, lag_set, W, H, lag_val, missing=True, dtype=None, device=0,
+                 lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1):
+        dtype = np.dtype(dtype if dtype is not None else W.dtype)
+        self.dtype = dtype
+        self.lib = lib = _lib(dtype)
+        if lib.trmf_b200_device_count() <= 0:
+            raise RuntimeError("trmf: no CUDA device visible; this solver is GPU-only (B200, sm_100a)")
+        self.lag_set = np.ascontiguousarray(np.sort(np.asarray(lag_set)), dtype=np.uint32)
+        self.pyY = Y if isinstance(Y, PyMatrix) else PyMatrix(Y, dtype)
+        self.pyW = PyMatrix(np.ascontiguousarray(W), dtype, major="row")
+        self.pyH = PyMatrix(np.ascontiguousarray(H), dtype, major="row")
+        self.pyL = PyMatrix(np.asfortranarray(lag_val), dtype, major="col")
+        self.T, self.k = self.pyW.py_buf["val"].shape
+        self.n = self.pyH.py_buf["val"].shape[0]
+        self.L = len(self.lag_set)
+        self.h = lib.trmf_b200_create(byref(self.pyY), self.lag_set.ctypes.data_as(POINTER(c_uint32)), self.L,
+                                      byref(self.pyW), byref(self.pyH), byref(self.pyL), int(bool(missing)), device)
+        if not self.h:
+            raise RuntimeError("trmf (CUDA) create failed: " + lib.trmf_b200_last_error().decode())
+        self.set_params(lambdaI, lambdaAR, lambdaLag)
+
+    @classmethod
+    def from_device(cls, dtype, T, n, nnz, k, row_ptr, col_idx, val_t, col_ptr, row_idx, val, lag_set,
+                    d_W, d_H, d_lag_val, device=0, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1):
+        """Wrap arrays already resident in HBM (integer device addresses)."""
+        self = cls.__new__(cls)
+        self.dtype = np.dtype(dtype)
+        self.lib = lib = _lib(dtype)
+        self.lag_set = np.ascontiguousarray(np.sort(np.asarray(lag_set)), dtype=np.uint32)
+        self.T, self.n, self.k, self.L = int(T), int(n), int(k), len(self.lag_set)
+        self.h = lib.trmf_b200_create_device(T, n, nnz, k, row_ptr, col_idx, val_t, col_ptr, row_idx, val,
+                                             self.lag_set.ctypes.data_as(POINTER(c_uint32)), self.L,
+                                             d_W, d_H, d_lag_val, device)
+        if not self.h:
+            raise RuntimeError("trmf (CUDA) create_device failed: " + lib.trmf_b200_last_error().decode())
+        self.set_params(lambdaI, lambdaAR, lambdaLag)
+        return self
+
+    def set_params(self, lambdaI, lambdaAR, lambdaLag):
+        _check(self.lib, self.lib.trmf_b200_set_params(self.h, lambdaI, lambdaAR, lambdaLag), "set_params")
+
+    def set_stream(self, cuda_stream):
+        _check(self.lib, self.lib.trmf_b200_set_stream(self.h, cuda_stream), "set_stream")
+
+    def enable_timing(self, on=True):
+        self.lib.trmf_b200_enable_timing(self.h, int(on))
+
+    def f_update(self):
+        _check(self.lib, self.lib.trmf_b200_f_update(self.h), "f_update")
+
+    def x_update(self):
+        _check(self.lib, self.lib.trmf_b200_x_update(self.h), "x_update")
+
+    def lag_update(self):
+        _check(self.lib, self.lib.trmf_b200_lag_update(self.h), "lag_update")
+
+    def train(self, max_iter=10, period_W=1, period_H=1, period_Lag=2, verbose=0):
+        _check(self.lib, self.lib.trmf_b200_train(self.h, max_iter, period_W, period_H, period_Lag, verbose), "train")
+
+    def sync(self):
+        _check(self.lib, self.lib.trmf_b200_sync(self.h), "sync")
+
+    def stat(self, name):
+        return self.lib.trmf_b200_stat(self.h, STAT[name])
+
+    def download(self):
+        W = np.empty((self.T, self.k), dtype=self.dtype, order="C")
+        H = np.empty((self.n, self.k), dtype=self.dtype, order="C")
+        Lv = np.empty((self.L, self.k), dtype=self.dtype, order="F")
+        _check(self.lib, self.lib.trmf_b200_download(self.h, W.ctypes.data, H.ctypes.data, Lv.ctypes.data), "download")
+        return W, H, Lv
+
+    def upload(self, W=None, H=None, lag_val=None):
+        keep = []
+
+        def ptr(a, order):
+            if a is None:
+                return None
+            a = np.asarray(a, dtype=self.dtype, order=order)
+            keep.append(a)
+            return a.ctypes.data
+        _check(self.lib, self.lib.trmf_b200_upload(self.h, ptr(W, "C"), ptr(H, "C"), ptr(lag_val, "F")), "upload")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.trmf_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

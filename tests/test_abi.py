@@ -1,0 +1,143 @@
+"""CPU tests of the drop-in boundary: the shared libraries load, export every
+symbol include/trmf_b200.h declares, PyMatrix has the reference's 80-byte layout,
+and the product fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import trmf
+from trmf.rf_util import PyMatrix
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "trmf_b200.h")
+CORELIB = os.path.join(ROOT, "exp-trmf-nips16_b200", "trmf", "corelib")
+
+
+def declared_symbols():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = set(re.findall(r"\b(c_trmf_train|trmf_b200_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
+
+
+def test_header_declares_the_reference_entry_point():
+    syms = declared_symbols()
+    assert "c_trmf_train" in syms and len(syms) >= 20
+
+
+@pytest.mark.parametrize("lib", ["trmf_float32.so", "trmf_float64.so"])
+def test_library_exports_every_declared_symbol(lib):
+    dll = ctypes.CDLL(os.path.join(CORELIB, lib))
+    for name in declared_symbols():
+        assert hasattr(dll, name), "{} does not export {}".format(lib, name)
+    dll.trmf_b200_value_bytes.restype = ctypes.c_int
+    assert dll.trmf_b200_value_bytes() == (4 if "32" in lib else 8)
+
+
+def test_pymatrix_layout_is_the_reference_pod():
+    # rf_util.py:41-52 / rf_matrix.h:3407-3415: 80 bytes, fixed offsets
+    assert ctypes.sizeof(PyMatrix) == 80
+    want = dict(rows=0, cols=8, nnz=16, row_ptr=24, col_ptr=32, row_idx=40, col_idx=48, val=56, val_t=64, type=72)
+    for name, off in want.items():
+        assert getattr(PyMatrix, name).offset == off
+
+
+def test_pymatrix_sparse_twin_storage_is_bit_exact():
+    rng = np.random.RandomState(0)
+    A = sps.random(37, 23, density=0.3, random_state=rng, format="csr")
+    A.data[:] = rng.randn(A.nnz)
+    pm = PyMatrix(A, np.float32)
+    csr, csc = sps.csr_matrix(A), sps.csc_matrix(A)
+    csr.sort_indices(); csc.sort_indices()
+    b = pm.py_buf
+    assert pm.type == PyMatrix.SPARSE and pm.nnz == A.nnz and (pm.rows, pm.cols) == (37, 23)
+    assert b["row_ptr"].dtype == np.uint64 and b["col_idx"].dtype == np.uint32
+    assert np.array_equal(b["row_ptr"], csr.indptr) and np.array_equal(b["col_idx"], csr.indices)
+    assert np.array_equal(b["col_ptr"], csc.indptr) and np.array_equal(b["row_idx"], csc.indices)
+    assert np.array_equal(b["val_t"], csr.data.astype(np.float32))
+    assert np.array_equal(b["val"], csc.data.astype(np.float32))
+    # empty and ragged
+    E = PyMatrix(sps.csr_matrix((5, 7)), np.float64)
+    assert E.nnz == 0 and np.array_equal(E.py_buf["row_ptr"], np.zeros(6, np.uint64))
+
+
+def test_pymatrix_dense_majors():
+    W = np.zeros((6, 3), order="C")
+    L = np.zeros((4, 3), order="F")
+    assert PyMatrix(W, np.float32).type == PyMatrix.DENSE_ROWMAJOR
+    assert PyMatrix(L, np.float32).type == PyMatrix.DENSE_COLMAJOR
+    assert PyMatrix(np.zeros((6, 1)), np.float32, major="row").type == PyMatrix.DENSE_ROWMAJOR
+    assert PyMatrix(np.zeros((1, 3), order="F"), np.float32, major="col").type == PyMatrix.DENSE_COLMAJOR
+
+
+def test_model_initialize_follows_the_reference_stream():
+    # trmf.py:224-236: seed, then W ~ rand, H ~ rand, lag_val ~ randn in that order
+    Y = np.zeros((30, 11), dtype=np.float64)
+    m = trmf.Model.initialize(Y, [5, 1, 2], 4, seed=7)
+    np.random.seed(7)
+    W = np.random.rand(30, 4); H = np.random.rand(11, 4); L = np.random.randn(3, 4)
+    assert np.array_equal(m.W, W) and np.array_equal(m.H, H) and np.array_equal(m.lag_val, L)
+    assert m.lag_set.dtype == np.uint32 and list(m.lag_set) == [1, 2, 5]
+    assert m.W.flags.c_contiguous and m.lag_val.flags.f_contiguous
+    assert (m.m, m.n, m.k) == (30, 11, 4) and m.transform is None
+
+
+def test_forecast_and_warm_start():
+    d = trmf.Model.syn_gen(80, 9, 3, [1, 2, 4], seed=3, dtype=np.float64)
+    m = trmf.Model.initialize(d["Y"], d["lag_set"], 3, seed=0)
+    m.W[:] = d["W"]; m.H[:] = d["H"]; m.lag_val[:] = d["lag_val"]
+    Wn = m.latent_forecast(5)
+    lags = d["lag_set"].astype(int)
+    for i in range(80, 85):
+        assert np.allclose(Wn[i], (Wn[i - lags] * d["lag_val"]).sum(axis=0))
+    Yn, Wtail = m.forecast(5, threshold=None)
+    assert np.allclose(Yn, Wn[80:] @ d["H"].T) and np.allclose(Wtail, Wn[80:])
+    Yc, _ = m.forecast(5, threshold=0)
+    assert (Yc >= 0).all()
+    Y2 = np.vstack([d["Y"], Yn])
+    m2 = trmf.Model.initialize(Y2, d["lag_set"], 3, seed=0, warm_start_model=m)
+    assert np.allclose(m2.W, Wn) and np.array_equal(m2.H, m.H) and np.array_equal(m2.lag_val, m.lag_val)
+
+
+def test_transform_metrics_save_load(tmp_path):
+    rng = np.random.RandomState(0)
+    Y = rng.rand(40, 6) * 5 + 2
+    Y[:, 2] = 1.5  # zero std -> treated as 1 (trmf.py:86)
+    tr = trmf.NormalizedTransform(Y)
+    Z = tr.preprocess(Y)
+    assert np.allclose(Z.mean(axis=0)[[0, 1, 3]], 0) and np.allclose(tr.postprocess(Z), Y)
+    m = trmf.Model.initialize(Y, [1, 2], 3, seed=1, transform=True)
+    assert isinstance(m.transform, trmf.NormalizedTransform)
+    m.save(str(tmp_path / "mdl"))
+    m2 = trmf.Model.load(str(tmp_path / "mdl"))
+    assert np.array_equal(m2.W, m.W) and np.array_equal(m2.lag_val, m.lag_val) and m2.lag_val.flags.f_contiguous
+    assert np.allclose(m2.transform.a, m.transform.a)
+    met = trmf.Metrics.generate(Y[-10:], Y[-10:] * 1.1)
+    assert abs(met.nd - 0.1) < 1e-12 and abs(met.mape - 0.1) < 1e-12 and "nd=" in str(met)
+    assert trmf.Metrics.default().m_nd == 1e10
+
+
+def test_no_silent_cpu_fallback():
+    """Without a visible CUDA device train() must raise, never compute on the host."""
+    lib = trmf.trmf._clib.clib_float32
+    if lib.trmf_b200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    d = trmf.Model.syn_gen(50, 8, 2, [1, 2], seed=0)
+    m = trmf.Model.initialize(d["Y"], d["lag_set"], 2, seed=0)
+    W0 = m.W.copy()
+    with pytest.raises(RuntimeError, match="GPU-only"):
+        trmf.train(d["Y"], m, missing=False)
+    assert np.array_equal(m.W, W0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "exp-trmf-nips16_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("no oracle", ""), f

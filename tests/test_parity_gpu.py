@@ -1,0 +1,194 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through
+the C ABI, against (i) the golden vectors recorded from the compiled reference,
+(ii) the NumPy float64 oracle and (iii) the live reference library when
+oracle/_ref travelled to the box.
+
+Tolerances (relative Frobenius, per outer iteration started from identical
+factors -- SURVEY 8d "parity metric"):
+  * float64 library vs float64 reference/oracle: 1e-9 (same CG step count required);
+  * float32 library vs float64 reference on the fp32-rounded inputs: 1e-5, the
+    bar BASELINE.json's north_star states.  (The reference's own float32 build
+    is ~1e-5 from its float64 build, tests/test_oracle.py::test_fp32_reference_band,
+    which is why the float64 oracle is the yardstick.)
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import cases
+from conftest import load_golden
+from oracle import abi, trmf_numpy as tn
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CORELIB = os.path.join(ROOT, "exp-trmf-nips16_b200", "trmf", "corelib")
+TOL64 = 1e-9
+TOL32 = 1e-5
+
+
+def lib_path(dtype):
+    return os.path.join(CORELIB, "trmf_float64.so" if np.dtype(dtype) == np.float64 else "trmf_float32.so")
+
+
+def run_cuda(Y, lags, W, H, L, dtype, **kw):
+    return abi.run_train(lib_path(dtype), Y, lags, W, H, L, dtype=dtype, **kw)
+
+
+def _inputs(g):
+    T, n = int(g["T"]), int(g["n"])
+    Ysp = sps.csr_matrix((g["coo_val"], (g["coo_row"], g["coo_col"])), shape=(T, n))
+    return Ysp, g["Ydense"], g["lags"], g["W0"], g["H0"], g["L0"], tuple(g["lambdas"])
+
+
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("phase", list(cases.PHASES))
+def test_float64_matches_golden(name, mode, phase):
+    g = load_golden(name)
+    Ysp, Yd, lags, W0, H0, L0, (lI, lAR, lLag) = _inputs(g)
+    pW, pH, pL, iters = cases.PHASES[phase]
+    W, H, L = run_cuda(Ysp if mode == "sparse" else Yd, lags, W0, H0, L0, np.float64, lambdaI=lI, lambdaAR=lAR,
+                       lambdaLag=lLag, max_iter=iters, period_W=pW, period_H=pH, period_Lag=pL,
+                       missing=(mode == "sparse"))
+    key = "{}_{}_f64".format(mode, phase)
+    assert cases.rel(W, g[key + "_W"]) < TOL64
+    assert cases.rel(H, g[key + "_H"]) < TOL64
+    assert cases.rel(L, g[key + "_L"]) < TOL64
+
+
+@pytest.mark.parametrize("name", list(cases.GOLDEN_CASES))
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("phase", ["f_only", "x_only", "lag_only", "iter1"])
+def test_float32_within_1e5_of_float64_oracle(name, mode, phase):
+    """fp32 storage, identical (fp32-representable) inputs on both sides."""
+    g = load_golden(name)
+    Ysp, Yd, lags, W0, H0, L0, (lI, lAR, lLag) = _inputs(g)
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    Ysp32 = sps.csr_matrix((f32(Ysp.data), Ysp.indices, Ysp.indptr), shape=Ysp.shape)
+    Y32 = Ysp32 if mode == "sparse" else f32(Yd)
+    W0, H0, L0 = f32(W0), f32(H0), f32(L0)
+    pW, pH, pL, iters = cases.PHASES[phase]
+    kw = dict(lambdaI=lI, lambdaAR=lAR, lambdaLag=lLag, max_iter=iters, period_W=pW, period_H=pH, period_Lag=pL,
+              missing=(mode == "sparse"))
+    W, H, L = run_cuda(Y32, lags, W0, H0, L0, np.float32, **kw)
+    Y64 = Y32.astype(np.float64)
+    Wo, Ho, Lo = tn.train(Y64, lags, W0.astype(np.float64), H0.astype(np.float64), L0.astype(np.float64), **kw)
+    assert cases.rel(W, Wo) < TOL32
+    assert cases.rel(H, Ho) < TOL32
+    assert cases.rel(L, Lo) < TOL32
+
+
+@pytest.mark.parametrize("k,lags", [(40, [1, 7, 24]), (64, [1, 2, 3, 24]), (20, list(range(1, 25))), (13, [2, 9])])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_one_outer_iteration_medium(k, lags, dtype):
+    """Sizes where the warp/CTA tiling paths (many entries per row, k = 40 / 64,
+    odd k) are exercised; oracle = NumPy float64 and, if present, the live reference."""
+    p = cases.make_problem(700, 450, k, lags, 0.6, seed=100 + k)
+    cast = lambda a: np.asarray(a, dtype=dtype)
+    Y = sps.csr_matrix((cast(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    W0, H0, L0 = cast(p["W0"]), cast(p["H0"]), cast(p["L0"])
+    kw = dict(lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5, max_iter=1, period_Lag=1, missing=True)
+    W, H, L = run_cuda(Y, p["lags"], W0, H0, L0, dtype, **kw)
+    tr = []
+    Wo, Ho, Lo = tn.train(Y.astype(np.float64), p["lags"], W0.astype(np.float64), H0.astype(np.float64),
+                          L0.astype(np.float64), trace=tr, **kw)
+    tol = TOL64 if dtype == np.float64 else TOL32
+    assert cases.rel(H, Ho) < tol and cases.rel(W, Wo) < tol and cases.rel(L, Lo) < tol
+    if abi.ref_available(np.float64):
+        Wr, Hr, Lr = abi.run_reference(Y.astype(np.float64), p["lags"], W0, H0, L0, threads=4, **kw)
+        assert cases.rel(H, Hr) < tol and cases.rel(W, Wr) < tol and cases.rel(L, Lr) < tol
+
+
+def test_cg_step_count_and_objective_match_oracle():
+    from trmf.session import Session
+    p = cases.make_problem(500, 300, 16, [1, 4, 12], 0.5, seed=21)
+    lam = (0.5, 20.0, 0.5)
+    s = Session(p["Ysp"], p["lags"], p["W0"], p["H0"], p["L0"], missing=True, dtype=np.float64,
+                lambdaI=lam[0], lambdaAR=lam[1], lambdaLag=lam[2])
+    W, H, L = p["W0"], p["H0"], p["L0"]
+    for it in range(3):
+        s.f_update()
+        H = tn.f_update_sparse(sps.csc_matrix(p["Ysp"]), W, H, lam[0])
+        s.x_update()
+        info = {}
+        W = tn.x_update(tn.SparseLoss(p["Ysp"], H), W, p["lags"].astype(np.int64), L, lam[0], lam[1], info)
+        assert int(s.stat("cg_iters")) == info["cg_iter"]
+        assert bool(s.stat("accepted")) == info["accepted"]
+        assert abs(s.stat("f") - info["f"]) <= 1e-10 * abs(info["f"])
+        assert abs(s.stat("fnew") - info["fnew"]) <= 1e-10 * abs(info["fnew"])
+        s.lag_update()
+        L = tn.lag_update(W, p["lags"], lam[2])
+        Wg, Hg, Lg = s.download()
+        assert cases.rel(Wg, W) < TOL64 and cases.rel(Hg, H) < TOL64 and cases.rel(Lg, L) < TOL64
+    assert s.stat("kernel_launches") > 0
+    s.close()
+
+
+def test_empty_series_and_time_stamps_are_handled():
+    p = cases.make_problem(80, 50, 6, [1, 3], 0.5, seed=5)
+    W, H, L = run_cuda(p["Ysp"], p["lags"], p["W0"], p["H0"], p["L0"], np.float64, max_iter=1, missing=True,
+                       period_W=cases.BIG, period_Lag=cases.BIG)
+    assert np.array_equal(H[3], p["H0"][3])             # unobserved series keeps its row (trmf.cpp:374)
+    assert np.array_equal(W, p["W0"]) and np.array_equal(L, np.asfortranarray(p["L0"]))
+    # a completely empty Y: F untouched, X only regularised
+    E = sps.csr_matrix(p["Ysp"].shape, dtype=np.float64)
+    W2, H2, _ = run_cuda(E, p["lags"], p["W0"], p["H0"], p["L0"], np.float64, max_iter=1, missing=True)
+    Wo, Ho, _ = tn.train(E, p["lags"], p["W0"], p["H0"], p["L0"], max_iter=1, missing=True, period_Lag=1)
+    assert np.array_equal(H2, p["H0"]) and cases.rel(W2, Wo) < TOL64
+
+
+def test_series_permutation_equivariance():
+    """Permuting series permutes F rows and leaves X, lag_val unchanged (up to summation order)."""
+    p = cases.make_problem(200, 120, 10, [1, 5], 0.6, seed=9)
+    perm = np.random.RandomState(0).permutation(120)
+    kw = dict(lambdaI=0.3, lambdaAR=10.0, lambdaLag=0.3, max_iter=2, period_Lag=1, missing=True)
+    W1, H1, L1 = run_cuda(p["Ysp"], p["lags"], p["W0"], p["H0"], p["L0"], np.float64, **kw)
+    W2, H2, L2 = run_cuda(sps.csr_matrix(p["Ysp"][:, perm]), p["lags"], p["W0"], p["H0"][perm], p["L0"], np.float64, **kw)
+    assert cases.rel(H2, H1[perm]) < 1e-9 and cases.rel(W2, W1) < 1e-9 and cases.rel(L2, L1) < 1e-9
+
+
+def test_full_mask_sparse_equals_dense_mode():
+    """missing=0 and missing=1 with every cell observed agree."""
+    p = cases.make_problem(150, 60, 8, [1, 2, 7], 1.1, seed=13, empty_series=False, empty_time=False)
+    kw = dict(lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=2, period_Lag=1)
+    Ws, Hs, Ls = run_cuda(sps.csr_matrix(p["Y"]), p["lags"], p["W0"], p["H0"], p["L0"], np.float64, missing=True, **kw)
+    Wd, Hd, Ld = run_cuda(p["Y"], p["lags"], p["W0"], p["H0"], p["L0"], np.float64, missing=False, **kw)
+    Wc, Hc, Lc = run_cuda(np.asfortranarray(p["Y"]), p["lags"], p["W0"], p["H0"], p["L0"], np.float64, missing=False, **kw)
+    assert cases.rel(Ws, Wd) < 1e-8 and cases.rel(Hs, Hd) < 1e-8 and cases.rel(Ls, Ld) < 1e-8
+    assert cases.rel(Wc, Wd) < 1e-12 and cases.rel(Hc, Hd) < 1e-12
+
+
+def test_f_update_is_idempotent_given_fixed_x():
+    p = cases.make_problem(300, 200, 12, [1, 2], 0.4, seed=17)
+    kw = dict(lambdaI=0.5, max_iter=1, missing=True, period_W=cases.BIG, period_Lag=cases.BIG)
+    _, H1, _ = run_cuda(p["Ysp"], p["lags"], p["W0"], p["H0"], p["L0"], np.float64, **kw)
+    _, H2, _ = run_cuda(p["Ysp"], p["lags"], p["W0"], H1, p["L0"], np.float64, **kw)
+    assert np.array_equal(H1, H2)   # deterministic kernels: bitwise
+
+
+def test_dimension_errors_print_and_return(capfd):
+    p = cases.make_problem(40, 20, 4, [1, 2], 0.5, seed=1)
+    W, H, L = run_cuda(p["Ysp"], p["lags"], p["W0"][:-1], p["H0"], p["L0"], np.float64, max_iter=1, missing=True)
+    err = capfd.readouterr().err
+    assert "[ERR MSG]: Y.rows (40) != W.rows (39)" in err        # trmf.cpp:563-566
+    assert np.array_equal(W, p["W0"][:-1]) and np.array_equal(H, p["H0"])   # returned without training
+
+
+def test_python_surface_end_to_end():
+    """trmf.train / forecast / rolling_validate on the GPU, as a user of the reference would call them."""
+    import trmf
+    d = trmf.Model.syn_gen(400, 60, 6, [1, 2, 24], seed=0, dtype=np.float32)
+    Y = d["Y"] + 10
+    m = trmf.Model.initialize(Y, d["lag_set"], 8, seed=0)
+    before = float(((Y - m.W @ m.H.T) ** 2).sum())
+    trmf.train(Y, m, lambdaI=0.01, lambdaAR=0.001, lambdaLag=0.0001, max_iter=10, missing=False)
+    after = float(((Y - m.W @ m.H.T) ** 2).sum())
+    assert after < 1e-3 * before
+    Yn, _ = m.forecast(24)
+    assert Yn.shape == (24, 60) and np.isfinite(Yn).all()
+    met = trmf.rolling_validate(Y, d["lag_set"], k=8, window_size=12, nr_windows=3, lambdaI=0.01, lambdaAR=0.01,
+                                lambdaLag=0.1, max_iter=5, missing=True, threshold=None)
+    assert np.isfinite(met.nd) and met.nd < 0.5
