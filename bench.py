@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- TRMF ALS hot path on B200: observed entries / second per outer iteration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c2|c3|c4|c5]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one ALS outer iteration F -> X -> lag_val (reference trmf.cpp:647-693 with
+all periods 1), always started from the same initial factors so that every step, on
+either arm, does identical work.  Default workload = BASELINE.json configs[1]:
+synthetic Y, T = n = 10 000, k = 40, 10 % missing, lag_set {1,7,24}, fp32 storage.
+With N GPUs the series axis is sharded in slabs and grown with N (weak scaling:
+n = 10 000 * N, T fixed); rank r holds Y[:, slab_r] in both orientations and its rows
+of F; every Omega-proportional X-update pass ends in one NCCL all-reduce of the
+T x k partial.
+
+Printed JSON (rank 0, one line): value = device-resident throughput (Y already in
+HBM), e2e = the same step through the public host-buffer API (H2D of Y and factors,
+D2H of the factors inside the timed region), roofline = the F-update kernel against
+the measured HBM peak, cpu_baseline = the reference's own OpenMP solver
+(oracle/_ref, built from /root/reference by oracle/Makefile) on a bounded sample.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "exp-trmf-nips16_b200"))
+
+CONFIGS = {
+    # name: T, n (per GPU when weak), k, p_observed, lags, weak-scaled?
+    "c2": dict(T=10000, n=10000, k=40, p=0.9, lags=[1, 7, 24], weak=True,
+               name="synthetic Y n=10k T=10k k=40, 10% missing, lag_set={1,7,24}"),
+    "c3": dict(T=10560, n=963, k=40, p=0.9, lags=list(range(1, 25)) + [168, 336], weak=True,
+               name="traffic-shape n=963 T=10560 k=40 lag_set={1..24,168,336}, sparse p=0.9"),
+    "c4": dict(T=50000, n=100000, k=60, p=0.1, lags=[1, 7, 24], weak=False,
+               name="synthetic sparse n=100k T=50k k=60 nnz~5e8 (strong scaling)"),
+    "c5": dict(T=100000, n=1000000, k=64, p=0.02, lags=[1, 7, 24], weak=False,
+               name="synthetic n=1M T=100k k=64 nnz~2e9 (strong scaling)"),
+    "tiny": dict(T=2000, n=1500, k=40, p=0.9, lags=[1, 7, 24], weak=True, name="tiny smoke config"),
+}
+LAMBDAS = (0.5, 50.0, 0.5)   # rolling_validate defaults, reference trmf.py:303
+RANK_TRUE, NOISE, SEED = 8, 0.01, 20161205
+SAMPLE_SERIES = 2500          # CPU arms: first 2500 series of the workload (all T time stamps)
+
+# --------------------------------------------------------------------------
+# host twin of csrc/synth.cuh (bit-identical; verified by tests/test_synth_gpu.py)
+# --------------------------------------------------------------------------
+_M1, _M2 = np.uint64(0xbf58476d1ce4e5b9), np.uint64(0x94d049bb133111eb)
+_G, _C2 = np.uint64(0x9E3779B97F4A7C15), np.uint64(0x632BE59BD9B4E019)
+
+
+def _mix(x):
+    x = x ^ (x >> np.uint64(30)); x = x * _M1
+    x = x ^ (x >> np.uint64(27)); x = x * _M2
+    return x ^ (x >> np.uint64(31))
+
+
+def _key(seed, stream, idx):
+    s = np.uint64(stream)
+    return _mix(np.uint64(seed) + s * _G + _mix(idx + _C2 * (s + np.uint64(1))))
+
+
+def _normal(h):
+    m = np.uint64(0xffff)
+    ssum = ((h & m).astype(np.int64) + ((h >> np.uint64(16)) & m).astype(np.int64) +
+            ((h >> np.uint64(32)) & m).astype(np.int64) + ((h >> np.uint64(48)) & m).astype(np.int64) - 131072)
+    return ssum.astype(np.float64) * (1.7320508075688772 / 65536.0)
+
+
+def host_synth(T, n, n_total, col_offset, r, p, noise, seed, dtype, row_block=512):
+    """CSR (by time) + CSC (by series) of Y[:, col_offset:col_offset+n]; local column indices."""
+    import scipy.sparse as sps
+    with np.errstate(over="ignore"):
+        thresh = np.uint32(min(max(p * 16777216.0, 0.0), 16777216.0))
+        Wn = _normal(_key(seed, 1, (np.arange(T, dtype=np.uint64)[:, None] * np.uint64(64) + np.arange(r, dtype=np.uint64)[None, :])))
+        jg = np.arange(col_offset, col_offset + n, dtype=np.uint64)
+        Hn = _normal(_key(seed, 2, jg[:, None] * np.uint64(64) + np.arange(r, dtype=np.uint64)[None, :]))
+        rows, cols, vals = [], [], []
+        for i0 in range(0, T, row_block):
+            i1 = min(T, i0 + row_block)
+            cell = np.arange(i0, i1, dtype=np.uint64)[:, None] * np.uint64(n_total) + jg[None, :]
+            obs = (_key(seed, 4, cell) >> np.uint64(40)).astype(np.uint32) < thresh
+            ii, jj = np.nonzero(obs)
+            acc = np.zeros(len(ii))
+            for q in range(r):
+                acc = acc + Wn[i0 + ii, q] * Hn[jj, q]
+            z = _normal(_key(seed, 3, cell[ii, jj]))
+            acc = acc + noise * z
+            rows.append((ii + i0).astype(np.int32)); cols.append(jj.astype(np.int32)); vals.append(acc.astype(dtype))
+        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+    csr = sps.csr_matrix((vals, (rows, cols)), shape=(T, n))
+    csr.sort_indices()
+    csc = csr.tocsc()
+    csc.sort_indices()
+    return csr, csc
+
+
+def init_factors(T, n_total, k, L, dtype):
+    """Model.initialize's draws (reference trmf.py:231-236): W, H ~ U(0,1), lag_val ~ N(0,1)."""
+    rng = np.random.RandomState(0)
+    W = rng.rand(T, k).astype(dtype)
+    H = rng.rand(n_total, k).astype(dtype)
+    Lv = np.asfortranarray(rng.randn(L, k).astype(dtype))
+    return W, H, Lv
+
+
+# --------------------------------------------------------------------------
+# helpers
+# --------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(k):
+    """dram bytes per F-kernel launch from the committed ncu --set full capture, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "f_update_traffic.json")) as fh:
+            d = json.load(fh)
+        return d.get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def ref_lib(dtype):
+    from oracle import abi
+    p = abi.ref_lib_path(dtype)
+    return p if os.path.exists(p) else None
+
+
+def cpu_one_iteration(csr, lags, W0, H0, L0, dtype, threads):
+    """One outer iteration on the host: the compiled reference (kind 'reference') or,
+    if oracle/_ref did not travel, the NumPy oracle (kind 'port')."""
+    from oracle import abi, trmf_numpy as tn
+    kw = dict(lambdaI=LAMBDAS[0], lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2], max_iter=1, period_W=1, period_H=1,
+              period_Lag=1, missing=True)
+    lib = ref_lib(dtype)
+    if lib is not None:
+        hY = abi.HostMatrix(csr, dtype)
+        t0 = time.perf_counter()
+        out = abi.run_train(lib, hY, lags, W0, H0, L0, dtype=dtype, threads=threads, **kw)
+        return time.perf_counter() - t0, "reference", threads, out
+    t0 = time.perf_counter()
+    out = tn.train(csr.astype(np.float64), lags, W0, H0, L0, **kw)
+    return time.perf_counter() - t0, "port", 1, out
+
+
+def sample_problem(cfg, dtype, n_total):
+    ns = min(SAMPLE_SERIES, cfg["n"])
+    csr, _ = host_synth(cfg["T"], ns, n_total, 0, RANK_TRUE, cfg["p"], NOISE, SEED, dtype)
+    W0, H0, L0 = init_factors(cfg["T"], n_total, cfg["k"], len(cfg["lags"]), dtype)
+    return csr, W0, H0[:ns].copy(), L0, ns
+
+
+# --------------------------------------------------------------------------
+# reference arm
+# --------------------------------------------------------------------------
+def run_reference_arm(args, cfg, rank, world):
+    if rank != 0:
+        return
+    dtype = np.float32
+    n_total = cfg["n"] * (world if cfg["weak"] else 1)
+    threads = os.cpu_count() or 1
+    csr, W0, H0, L0, ns = sample_problem(cfg, dtype, n_total)
+    lags = np.array(cfg["lags"], dtype=np.uint32)
+    times, kind, cores = [], None, 1
+    for it in range(args.warmup + args.steps):
+        dt, kind, cores, _ = cpu_one_iteration(csr, lags, W0, H0, L0, dtype, threads)
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = csr.nnz / (ms * 1e-3)
+    sample = "first {} of {} series, all T={} time stamps, nnz={}; one outer iteration F->X->lag from the bench's initial factors".format(
+        ns, n_total, cfg["T"], csr.nnz)
+    line = {"impl": "reference", "metric": "observed entries/sec per ALS outer iter", "value": value, "unit": "entries/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak" if cfg["weak"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"], "T": cfg["T"], "n": n_total, "k": cfg["k"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------
+def run_b200_arm(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session, SynthDesc, _lib
+    import trmf
+
+    dtype = np.float32
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib(dtype)
+    T, k, lags = cfg["T"], cfg["k"], np.array(cfg["lags"], dtype=np.uint32)
+    n_total = cfg["n"] * (world if cfg["weak"] else 1)
+    # series slabs: equal widths (the synthetic mask is i.i.d., so this is nnz-balanced)
+    bounds = [n_total * r // world for r in range(world + 1)]
+    col0, n_loc = bounds[rank], bounds[rank + 1] - bounds[rank]
+
+    # ---- data straight into HBM ----
+    sd = SynthDesc()
+    rc = lib.trmf_b200_synth_generate(ctypes.byref(sd), T, n_loc, n_total, col0, RANK_TRUE, cfg["p"], NOISE, SEED, local_rank)
+    if rc != 0:
+        raise RuntimeError("synth_generate failed: " + lib.trmf_b200_last_error().decode())
+    nnz_loc = int(sd.nnz)
+    W0, H0, L0 = init_factors(T, n_total, k, len(lags), dtype)
+    H0 = np.ascontiguousarray(H0[col0:col0 + n_loc])
+    dW, dH, dL = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (W0, H0, np.ascontiguousarray(L0.T)))
+    # (lag_val is L x k col-major == k x L row-major == L0.T contiguous)
+    stream = torch.cuda.Stream(device=dev)
+    s = Session.from_device(dtype, T, n_loc, nnz_loc, k, sd.d_row_ptr, sd.d_col_idx, sd.d_val_t, sd.d_col_ptr,
+                            sd.d_row_idx, sd.d_val, lags, dW.data_ptr(), dH.data_ptr(), dL.data_ptr(), device=local_rank,
+                            lambdaI=LAMBDAS[0], lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2])
+    s.set_stream(stream.cuda_stream)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            buf = (ctypes.c_ubyte * 128)()
+            if lib.trmf_b200_nccl_unique_id(buf) != 0:
+                raise RuntimeError(lib.trmf_b200_last_error().decode())
+            uid = torch.tensor(list(buf), dtype=torch.uint8)
+        uid = uid.to(dev)
+        dist.broadcast(uid, 0)
+        idb = (ctypes.c_ubyte * 128)(*uid.cpu().tolist())
+        if lib.trmf_b200_dist_init(s.h, rank, world, idb) != 0:
+            raise RuntimeError(lib.trmf_b200_last_error().decode())
+    s.save_factors()
+    s.enable_timing(True)
+
+    def step():
+        s.restore_factors()
+        s.f_update()
+        s.x_update()
+        s.lag_update()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = s.stat("kernel_launches")
+    coll0 = s.stat("collectives")
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fk_ms, f_ms, x_ms, lag_ms, cg = [], [], [], [], []
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+            fk_ms.append(s.stat("f_kernel_ms")); f_ms.append(s.stat("f_ms")); x_ms.append(s.stat("x_ms"))
+            lag_ms.append(s.stat("lag_ms")); cg.append(int(s.stat("cg_iters")))
+        e1.record(stream)
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = e0.elapsed_time(e1)
+    launches = int(s.stat("kernel_launches") - launches0)
+    collectives = int(s.stat("collectives") - coll0)
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    nn = torch.tensor([float(nnz_loc)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(nn, op=dist.ReduceOp.SUM)
+    total_ms, nnz_total = float(t.item()), float(nn.item())
+    ms_per_step = total_ms / args.steps
+    value = nnz_total / (ms_per_step * 1e-3)
+
+    # ---- roofline of the F-update kernel (B_F = N(8+4k) + n(8+4k), fp32) ----
+    peak, peak_src = measured_hbm_peak()
+    bytes_f = nnz_loc * (8 + 4 * k) + n_loc * (8 + 4 * k)
+    fk = float(np.mean(fk_ms))
+    achieved = bytes_f / (fk * 1e-3) / 1e9
+    flops_f = nnz_loc * (k * k + 3 * k) + n_loc * (k ** 3 / 3 + 2 * k * k)
+    roofline = {"bound": "hbm", "kernel": "f_update (Gram + Cholesky per series)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(k), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_f, "kernel_ms": fk, "fp32_tflops": flops_f / (fk * 1e-3) / 1e12,
+                "entries_per_s": nnz_loc / (fk * 1e-3)}
+
+    # ---- end to end through the public host-buffer API ----
+    e2e = run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0, n_loc, nnz_loc, nnz_total)
+
+    s.close()
+    lib.trmf_b200_free_synth(ctypes.byref(sd))
+
+    line = None
+    if rank == 0:
+        line = {"metric": "observed entries/sec per ALS outer iter", "value": value, "unit": "entries/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak" if cfg["weak"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": cfg["name"], "T": T, "n": n_total, "k": k, "nnz": int(nnz_total), "lag_set": cfg["lags"],
+                           "lambdas": LAMBDAS, "sharding": "series slabs x{}".format(world),
+                           "l2": "inputs larger than L2 (Y = {:.2f} GB per GPU in two orientations); no flush".format(nnz_loc * 16 / 1e9),
+                           "step": "one outer iteration F->X->lag_val restarted from the same factors"},
+                "e2e": e2e, "gpu_launches": launches, "collectives": collectives, "clocks": clocks, "roofline": roofline,
+                "phase_ms": {"f_update": float(np.mean(f_ms)), "x_update": float(np.mean(x_ms)), "lag_update": float(np.mean(lag_ms))},
+                "cg_steps": cg}
+    return line
+
+
+def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_rank, lags, W0, H0, L0, n_loc, nnz_loc, nnz_total):
+    """Same step, host buffers in, host buffers out: N = 1 goes through the drop-in
+    `c_trmf_train`; N > 1 through the session API (create from host slab, one iteration, download)."""
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    import trmf
+    T, k = cfg["T"], cfg["k"]
+    dev = torch.device("cuda", local_rank)
+
+    def d2h(ptr, count, npdtype):
+        nbytes = count * np.dtype(npdtype).itemsize
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        if lib.trmf_b200_copy_to_host(t.data_ptr(), ptr, nbytes) != 0:
+            raise RuntimeError(lib.trmf_b200_last_error().decode())
+        return t, t.numpy()[:nbytes].view(npdtype)
+
+    keep = []
+    pm = PyMatrix(None)
+    pm.py_buf = {}
+    pm.dtype = np.dtype(dtype)
+    pm.rows, pm.cols, pm.nnz, pm.type = T, n_loc, nnz_loc, PyMatrix.SPARSE
+    fields = dict(PyMatrix._fields_)
+    for name, ptr, cnt, dt in (("row_ptr", sd.d_row_ptr, T + 1, np.uint64), ("col_idx", sd.d_col_idx, nnz_loc, np.uint32),
+                               ("val_t", sd.d_val_t, nnz_loc, dtype), ("col_ptr", sd.d_col_ptr, n_loc + 1, np.uint64),
+                               ("row_idx", sd.d_row_idx, nnz_loc, np.uint32), ("val", sd.d_val, nnz_loc, dtype)):
+        t, a = d2h(ptr, cnt, dt)
+        keep.append(t)
+        pm.py_buf[name] = a
+        setattr(pm, name, a.ctypes.data if fields[name] is ctypes.c_void_p else a.ctypes.data_as(fields[name]))
+    h2d = sum(a.nbytes for a in pm.py_buf.values()) + W0.nbytes + H0.nbytes + L0.nbytes
+    d2h_bytes = W0.nbytes + H0.nbytes + L0.nbytes
+    steps = max(1, min(args.steps, 5))
+    times = []
+    for it in range(1 + steps):   # 1 warm-up
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        if world == 1:
+            m = trmf.Model(pyW=PyMatrix(W0, dtype, major="row"), pyH=PyMatrix(H0, dtype, major="row"),
+                           pylag_val=PyMatrix(L0, dtype, major="col"), lag_set=lags)
+            trmf.trmf._clib.train(pm, lags, m.pyW, m.pyH, m.pylag_val, warm_start=True, lambdaI=LAMBDAS[0],
+                                  lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2], max_iter=1, period_W=1, period_H=1,
+                                  period_Lag=1, threads=1, missing=True, verbose=0)
+            _ = float(m.W[0, 0])
+        else:
+            se = Session(pm, lags, W0, H0, L0, missing=True, dtype=dtype, device=local_rank, lambdaI=LAMBDAS[0],
+                         lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2])
+            if lib.trmf_b200_dist_attach(se.h, s_dev.h) != 0:
+                raise RuntimeError(lib.trmf_b200_last_error().decode())
+            se.train(max_iter=1, period_W=1, period_H=1, period_Lag=1)
+            Wn, Hn, Ln = se.download()
+            se.close()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        if it >= 1:
+            times.append(float(tt.item()))
+    sec = float(np.mean(times))
+    return {"value": nnz_total / sec, "unit": "entries/s", "ms_per_step": 1e3 * sec, "steps": steps,
+            "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes),
+            "api": "c_trmf_train (host PyMatrix buffers, pinned)" if world == 1 else "trmf.session.Session(host slab) + NCCL"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, rank, world)
+        return
+
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    line = run_b200_arm(args, cfg, rank, world, local_rank)
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            dtype = np.float32
+            csr, W0, H0, L0, ns = sample_problem(cfg, dtype, cfg["n"])
+            threads = os.cpu_count() or 1
+            dt, kind, cores, _ = cpu_one_iteration(csr, np.array(cfg["lags"], dtype=np.uint32), W0, H0, L0, dtype, threads)
+            line["cpu_baseline"] = {"value": csr.nnz / dt, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": dt,
+                                    "sample": "first {} of {} series, all T={} time stamps, nnz={}; one outer iteration".format(
+                                        ns, cfg["n"], cfg["T"], csr.nnz)}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,7 @@ struct trmf_b200_session {
 
     // factors
     V *W = nullptr, *H = nullptr, *th = nullptr;
+    V *W_sv = nullptr, *H_sv = nullptr, *th_sv = nullptr;   // save_factors() snapshot
     bool own_factors = false;
     std::vector<uint32_t> lags;
     uint32_t *lags_dev = nullptr;
@@ -98,6 +99,9 @@ struct trmf_b200_session {
     // multi-GPU
     int rank = 0, world = 1;
     void *nccl_comm = nullptr;
+    bool own_comm = false;
+    V *part_tk = nullptr;         // this rank's partial of a T x k pass, all-reduced in place
+    unsigned long long collectives = 0;
 
     double lambdaI = 0.1, lambdaAR = 0.1, lambdaLag = 0.1;
 
@@ -110,6 +114,11 @@ struct trmf_b200_session {
     double st_delta = 0, st_rnorm = 0;
 };
 typedef trmf_b200_session S;
+
+// multi-GPU helpers, defined in extras.cuh
+static int dist_allreduce_v(S *s, V *buf, size_t count);
+static int dist_allreduce_f64(S *s, double *buf, size_t count);
+static void dist_teardown(S *s);
 
 // `kern` may be a parenthesised template-id; it is bound to a pointer first.
 #define LAUNCH(s, kern, grid, block, smem, ...)                                           \
@@ -209,12 +218,15 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    dist_teardown(s);
+    cudaFree(s->part_tk);
     if (s->own_Y) {
         cudaFree(s->row_ptr); cudaFree(s->col_ptr); cudaFree(s->col_idx); cudaFree(s->row_idx);
         cudaFree(s->val_t); cudaFree(s->val); cudaFree(s->Yd);
     }
     if (s->own_factors) { cudaFree(s->W); cudaFree(s->H); cudaFree(s->th); }
     cudaFree(s->lags_dev);
+    cudaFree(s->W_sv); cudaFree(s->H_sv); cudaFree(s->th_sv);
     cudaFree(s->g); cudaFree(s->s); cudaFree(s->r); cudaFree(s->d); cudaFree(s->Hd); cudaFree(s->wnew);
     cudaFree(s->rho); cudaFree(s->scal); cudaFree(s->part); cudaFree(s->ticket);
     cudaFree(s->YH); cudaFree(s->tmp_nk); cudaFree(s->HTH); cudaFree(s->WTW); cudaFree(s->YtW); cudaFree(s->Cpart);
@@ -368,7 +380,7 @@ static int gemm(S *s, const TA *A, size_t sm, size_t sk, const TB *B, size_t M, 
 
 template <int MODE>
 static int sparse_pass(S *s, const uint64_t *ptr, const uint32_t *col, const V *val, const V *Hm, const V *Sv, V *out,
-                       size_t rows, int fslot) {
+                       size_t rows, int fslot, bool accum = true) {
     const int k = s->k;
     const int WARPS = 4;
     const size_t smem = sparse_pass_smem(k, WARPS);
@@ -377,7 +389,7 @@ static int sparse_pass(S *s, const uint64_t *ptr, const uint32_t *col, const V *
 #define SP_LAUNCH(KR)                                                                                         \
     do {                                                                                                      \
         CUDA_TRY(cudaFuncSetAttribute((sparse_pass_kernel<MODE, KR, WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        LAUNCH(s, (sparse_pass_kernel<MODE, KR, WARPS>), grid, WARPS * 32, smem, ptr, col, val, Hm, Sv, out, k, rows, 0u, \
+        LAUNCH(s, (sparse_pass_kernel<MODE, KR, WARPS>), grid, WARPS * 32, smem, ptr, col, val, Hm, Sv, out, k, rows, accum, \
                s->part, s->ticket, fout);                                                                     \
     } while (0)
     if (k <= 32) SP_LAUNCH(1);
@@ -425,6 +437,7 @@ static int fun_launch(S *s, const V *v) {
     LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, v, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
     if (s->missing) {
         if (sparse_pass<MODE_FUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, v, nullptr, s->T, SC_FLOSS)) return 1;
+        if (dist_allreduce_f64(s, s->scal + SC_FLOSS, 1)) return 1;   // sum of the per-slab losses
     } else {
         // 0.5 trYTY + 0.5 <W^T W, HTH> - <YH, W>    (trmf.cpp:189-197)
         const int k = s->k;
@@ -440,9 +453,21 @@ static double fun_combine(const S *s) {
     return h[SC_FBASE] + 0.5 * h[SC_TMP2] + 0.5 * h[SC_TMP] - h[SC_FLOSS];
 }
 
+// loss part of grad / Hv over this rank's series slab; with several ranks the T x k
+// partials are summed by one ncclAllReduce and then added to the (replicated) base term
+template <int MODE>
+static int loss_pass(S *s, const V *v, V *out) {
+    if (s->world == 1) return sparse_pass<MODE>(s, s->row_ptr, s->col_idx, s->val_t, s->H, v, out, s->T, -1, true);
+    const size_t tk = s->T * (size_t)s->k;
+    if (sparse_pass<MODE>(s, s->row_ptr, s->col_idx, s->val_t, s->H, v, s->part_tk, s->T, -1, false)) return 1;
+    if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
+    LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, out, 1.0, s->part_tk, 0.0, (const V *)nullptr, out, tk);
+    return 0;
+}
+
 static int grad_launch(S *s, const V *w, V *g) {
     if (base_apply(s, w, g)) return 1;
-    if (s->missing) return sparse_pass<MODE_GRAD>(s, s->row_ptr, s->col_idx, s->val_t, s->H, w, g, s->T, -1);
+    if (s->missing) return loss_pass<MODE_GRAD>(s, w, g);
     // G += -YH + W HTH   (trmf.cpp:204-206)
     const size_t tk = s->T * (size_t)s->k;
     LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, g, -1.0, s->YH, 0.0, (const V *)nullptr, g, tk);
@@ -451,7 +476,7 @@ static int grad_launch(S *s, const V *w, V *g) {
 
 static int hv_launch(S *s, const V *d, V *Hd) {
     if (base_apply(s, d, Hd)) return 1;
-    if (s->missing) return sparse_pass<MODE_HV>(s, s->row_ptr, s->col_idx, s->val_t, s->H, d, Hd, s->T, -1);
+    if (s->missing) return loss_pass<MODE_HV>(s, d, Hd);
     return gemm<V, double, V>(s, d, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, Hd, 1.0, 0.0, Hd);
 }
 
@@ -630,7 +655,10 @@ extern "C" int trmf_b200_train(S *s, int32_t max_iter, int32_t period_W, int32_t
         double nv = 0;
         if (iter % period_H == 0) {
             if (trmf_b200_f_update(s)) return 1;
-            if (verbose) { if (sq_norm(s, s->H, nk, &nv)) return 1; fprintf(stderr, ">> iter %d F %g\n", iter, nv); }
+            if (verbose) {
+                if (dot(s, s->H, s->H, nk, SC_TMP) || dist_allreduce_f64(s, s->scal + SC_TMP, 1) || read_scalars(s)) return 1;
+                fprintf(stderr, ">> iter %d F %g\n", iter, s->h_scal[SC_TMP]);
+            }
         }
         if (iter % period_W == 0) {
             if (trmf_b200_x_update(s)) return 1;
@@ -668,6 +696,25 @@ extern "C" int trmf_b200_upload(S *s, const void *W, const void *H, const void *
     return 0;
 }
 
+extern "C" int trmf_b200_save_factors(S *s) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    const size_t tk = s->T * (size_t)s->k, nk = s->n * (size_t)s->k, lk = (size_t)s->L * s->k;
+    if (!s->W_sv && (dev_alloc(&s->W_sv, tk) || dev_alloc(&s->H_sv, nk) || dev_alloc(&s->th_sv, lk))) return 1;
+    CUDA_TRY(cudaMemcpyAsync(s->W_sv, s->W, tk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->H_sv, s->H, nk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->th_sv, s->th, lk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+extern "C" int trmf_b200_restore_factors(S *s) {
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (!s->W_sv) return fail("restore_factors called before save_factors");
+    const size_t tk = s->T * (size_t)s->k, nk = s->n * (size_t)s->k, lk = (size_t)s->L * s->k;
+    CUDA_TRY(cudaMemcpyAsync(s->W, s->W_sv, tk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->H, s->H_sv, nk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(s->th, s->th_sv, lk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
+    return 0;
+}
+
 extern "C" double trmf_b200_stat(S *s, int32_t which) {
     switch (which) {
         case TRMF_STAT_CG_ITERS: return s->st_cg;
@@ -682,6 +729,7 @@ extern "C" double trmf_b200_stat(S *s, int32_t which) {
         case TRMF_STAT_F_KERNEL_MS: return s->ms_fk;
         case TRMF_STAT_PRERED: return s->st_prered;
         case TRMF_STAT_ACTRED: return s->st_actred;
+        case TRMF_STAT_COLLECTIVES: return (double)s->collectives;
     }
     return NAN;
 }

@@ -92,7 +92,7 @@ template <int MODE, int KR, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ col,
                    const V *__restrict__ val, const V *__restrict__ H, const V *__restrict__ S,
-                   V *__restrict__ out, int k, size_t T, uint32_t col_base,
+                   V *__restrict__ out, int k, size_t T, bool accum,
                    double *part, unsigned *ticket, double *fout) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int ks = k | 1;   // odd stride: conflict-free column walks
@@ -114,7 +114,7 @@ sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict_
         for (uint64_t base = lo; base < hi; base += 32) {
             const uint64_t e = base + lane;
             const bool valid = e < hi;
-            const uint32_t j = valid ? col[e] - col_base : 0u;
+            const uint32_t j = valid ? col[e] : 0u;
             const V y = (valid && MODE != MODE_HV) ? val[e] : (V)0;
             const int cnt = (int)((hi - base) < 32 ? (hi - base) : 32);
             __syncwarp();
@@ -154,7 +154,7 @@ sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict_
             for (int q = 0; q < KR; ++q) {
                 const int t = lane + 32 * q;
                 if (t < k) {
-                    if (MODE == MODE_SPMM) out[i * k + t] = (V)accd[q];
+                    if (MODE == MODE_SPMM || !accum) out[i * k + t] = (V)accd[q];
                     else out[i * k + t] = (V)((double)out[i * k + t] + accd[q]);
                 }
             }

@@ -14,7 +14,7 @@ from .rf_util import PyMatrix
 from .trmf import _clib
 
 STAT = dict(cg_iters=0, accepted=1, f=2, fnew=3, gnorm=4, kernel_launches=5,
-            f_ms=6, x_ms=7, lag_ms=8, f_kernel_ms=9, prered=10, actred=11)
+            f_ms=6, x_ms=7, lag_ms=8, f_kernel_ms=9, prered=10, actred=11, collectives=12)
 
 
 class SynthDesc(ctypes.Structure):
@@ -41,7 +41,7 @@ def _lib(dtype):
     lib.trmf_b200_destroy.argtypes = [c_void_p]
     lib.trmf_b200_set_params.argtypes = [c_void_p, c_double, c_double, c_double]
     lib.trmf_b200_set_stream.argtypes = [c_void_p, c_void_p]
-    for name in ("f_update", "x_update", "lag_update", "sync"):
+    for name in ("f_update", "x_update", "lag_update", "sync", "save_factors", "restore_factors"):
         getattr(lib, "trmf_b200_" + name).argtypes = [c_void_p]
     lib.trmf_b200_train.argtypes = [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]
     lib.trmf_b200_download.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
@@ -51,6 +51,8 @@ def _lib(dtype):
     lib.trmf_b200_enable_timing.argtypes = [c_void_p, c_int32]
     lib.trmf_b200_nccl_unique_id.argtypes = [c_void_p]
     lib.trmf_b200_dist_init.argtypes = [c_void_p, c_int32, c_int32, c_void_p]
+    lib.trmf_b200_dist_attach.argtypes = [c_void_p, c_void_p]
+    lib.trmf_b200_copy_to_host.argtypes = [c_void_p, c_void_p, c_uint64]
     lib.trmf_b200_allgather_H.argtypes = [c_void_p, c_void_p, POINTER(c_uint64)]
     lib.trmf_b200_synth_generate.argtypes = [POINTER(SynthDesc), c_uint64, c_uint64, c_uint64, c_uint64, c_uint32,
                                              c_double, c_double, c_uint64, c_int32]
@@ -130,6 +132,12 @@ class Session(object):
 
     def train(self, max_iter=10, period_W=1, period_H=1, period_Lag=2, verbose=0):
         _check(self.lib, self.lib.trmf_b200_train(self.h, max_iter, period_W, period_H, period_Lag, verbose), "train")
+
+    def save_factors(self):
+        _check(self.lib, self.lib.trmf_b200_save_factors(self.h), "save_factors")
+
+    def restore_factors(self):
+        _check(self.lib, self.lib.trmf_b200_restore_factors(self.h), "restore_factors")
 
     def sync(self):
         _check(self.lib, self.lib.trmf_b200_sync(self.h), "sync")

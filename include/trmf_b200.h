@@ -116,6 +116,10 @@ int trmf_b200_download(trmf_b200_session *s, void *W, void *H, void *lag_val);
 /* Replace factors from HOST buffers (any may be NULL). */
 int trmf_b200_upload(trmf_b200_session *s, const void *W, const void *H, const void *lag_val);
 int trmf_b200_sync(trmf_b200_session *s);
+/* Keep a device-side copy of the current factors / put it back (benchmark:
+ * every timed step restarts from the same (W, H, lag_val)). */
+int trmf_b200_save_factors(trmf_b200_session *s);
+int trmf_b200_restore_factors(trmf_b200_session *s);
 
 /* Introspection for parity tests and the benchmark. */
 enum {
@@ -130,7 +134,8 @@ enum {
     TRMF_STAT_LAG_MS = 8,        /* ... last lag_update                                   */
     TRMF_STAT_F_KERNEL_MS = 9,   /* ... the Gram+Cholesky kernel alone inside f_update    */
     TRMF_STAT_PRERED = 10,
-    TRMF_STAT_ACTRED = 11
+    TRMF_STAT_ACTRED = 11,
+    TRMF_STAT_COLLECTIVES = 12   /* NCCL collectives issued by this session so far            */
 };
 double trmf_b200_stat(trmf_b200_session *s, int32_t which);
 /* Enable per-phase CUDA-event timing (off by default: it inserts stream syncs). */
@@ -145,6 +150,8 @@ int trmf_b200_enable_timing(trmf_b200_session *s, int32_t on);
  * (torch.distributed in bench.py). */
 int trmf_b200_nccl_unique_id(void *out128);
 int trmf_b200_dist_init(trmf_b200_session *s, int32_t rank, int32_t world, const void *unique_id128);
+/* Share the communicator of `owner` with another session of this process (non-owning). */
+int trmf_b200_dist_attach(trmf_b200_session *s, trmf_b200_session *owner);
 /* all-gather of the per-rank H slabs into a host/device buffer on every rank
  * (rows in global series order); `counts[r]` = rows of rank r. */
 int trmf_b200_allgather_H(trmf_b200_session *s, void *d_H_full, const uint64_t *counts);
@@ -163,6 +170,8 @@ typedef struct {
 int  trmf_b200_synth_generate(trmf_b200_synth *out, uint64_t T, uint64_t n, uint64_t n_total, uint64_t col_offset,
                               uint32_t rank_true, double p_observed, double noise, uint64_t seed, int32_t device);
 void trmf_b200_free_synth(trmf_b200_synth *s);
+/* plain cudaMemcpy device -> host (so that host programs need no CUDA binding of their own) */
+int  trmf_b200_copy_to_host(void *dst_host, const void *src_device, uint64_t bytes);
 
 #ifdef __cplusplus
 }

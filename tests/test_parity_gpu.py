@@ -189,6 +189,23 @@ def test_python_surface_end_to_end():
     assert after < 1e-3 * before
     Yn, _ = m.forecast(24)
     assert Yn.shape == (24, 60) and np.isfinite(Yn).all()
-    met = trmf.rolling_validate(Y, d["lag_set"], k=8, window_size=12, nr_windows=3, lambdaI=0.01, lambdaAR=0.01,
-                                lambdaLag=0.1, max_iter=5, missing=True, threshold=None)
-    assert np.isfinite(met.nd) and met.nd < 0.5
+    # rolling_validate: same host loop, CUDA trainer vs oracle trainer swapped in behind _clib.train
+    Y64 = Y.astype(np.float64)
+    kw = dict(k=8, window_size=12, nr_windows=3, lambdaI=0.01, lambdaAR=0.01, lambdaLag=0.1, max_iter=5,
+              missing=True, threshold=None)
+    met = trmf.rolling_validate(Y64, d["lag_set"], **kw)
+
+    def oracle_train(pyY, lag_set, pyW, pyH, pylag_val, warm_start=True, threads=1, verbose=0, **tk):
+        b = pyY.py_buf
+        Ycsr = sps.csr_matrix((b["val_t"], b["col_idx"], b["row_ptr"].astype(np.int64)), shape=(pyY.rows, pyY.cols))
+        W, H, L = tn.train(Ycsr, lag_set, pyW.py_buf["val"], pyH.py_buf["val"], pylag_val.py_buf["val"], **tk)
+        pyW.py_buf["val"][:] = W; pyH.py_buf["val"][:] = H; pylag_val.py_buf["val"][:] = L
+
+    real_train = trmf.trmf._clib.train
+    trmf.trmf._clib.train = oracle_train
+    try:
+        met_o = trmf.rolling_validate(Y64, d["lag_set"], **kw)
+    finally:
+        trmf.trmf._clib.train = real_train
+    for a, b in zip(met, met_o):
+        assert np.isfinite(a) and abs(a - b) <= 1e-6 * max(1.0, abs(b))
