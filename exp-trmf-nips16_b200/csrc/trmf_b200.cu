@@ -490,9 +490,9 @@ extern "C" int trmf_b200_f_update(S *s) {
     const int k = s->k;
     if (s->missing) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
-        if (f_update_tiled_supported(k)) {
+        if (f_update_tiled_supported(k) && (((uintptr_t)s->W) & 15) == 0 && !getenv("TRMF_B200_GENERIC_F")) {
             if (f_update_tiled_launch(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, k, s->lambdaI,
-                                      (uint32_t)s->n, &s->launches))
+                                      (uint32_t)s->n, s->ticket + 1, &s->launches))
                 return fail("f_update_tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             const int ENT = 32;
