@@ -45,6 +45,7 @@ template <int NB> struct Cfg {
     static constexpr int FL = (128 / U) > 0 ? (128 / U) : 1;   // tiles between fp32 -> fp64 flushes
     static constexpr int FBUF = G * B * 32;    // floats: half of every lane's 8x8 block
     static constexpr int RBUF = 32 * KP;       // floats: rhs partials of the 32 rhs lanes
+    static constexpr int VALS = (STAGES * ET + 3) / 4 * 4;   // staged Y values, padded so fbuf stays 16-B aligned
 };
 
 __device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
@@ -63,17 +64,22 @@ static size_t smem_bytes(int k) {
     typedef Cfg<NB> C;
     size_t dbl = (size_t)(k + 1) * (k + 1) + k;
     dbl = (dbl + 1) & ~(size_t)1;   // keep the float region 16-B aligned
-    return dbl * sizeof(double) + sizeof(float) * ((size_t)C::STAGES * C::ET * C::RS + C::STAGES * C::ET + C::FBUF + C::RBUF);
+    return dbl * sizeof(double) + sizeof(float) * ((size_t)C::STAGES * C::ET * C::RS + C::VALS + C::FBUF + C::RBUF);
 }
 
 // index of member m (0..7) of set R(t): chunk t then chunk t + NB
 template <int NB> __device__ __forceinline__ int set_index(int t, int m) { return m < 4 ? 4 * t + m : 4 * (t + NB) + (m - 4); }
 
-template <int NB>
+// SOLVE = true : F-update -- solve (Gram + lambda I) f = rhs and store the k results in F[j].
+// SOLVE = false: "store" mode used by the X-update (rows = time stamps, X = the series factor):
+//                the k x k Gram (full symmetric square, fp32) goes to Gout[j] and the rhs to
+//                F[j]; rows without entries get zeros.  The Hessian-vector products of the CG
+//                solve then read these Grams instead of re-walking Omega (x_update.cuh).
+template <int NB, bool SOLVE>
 __global__ void __launch_bounds__(NT, 2)
 f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
-                      const float *__restrict__ X, float *__restrict__ F, int k, double lambda, uint32_t nseries,
-                      unsigned *__restrict__ queue) {
+                      const float *__restrict__ X, float *__restrict__ F, float *__restrict__ Gout, int k, double lambda,
+                      uint32_t nseries, unsigned *__restrict__ queue) {
     typedef Cfg<NB> C;
     constexpr int KP = C::KP, B = C::B, G = C::G, U = C::U, ET = C::ET, RS = C::RS, STAGES = C::STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -84,7 +90,7 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
     dbl = (dbl + 1) & ~(size_t)1;
     float *tiles = reinterpret_cast<float *>(A + dbl);           // STAGES x ET x RS
     float *vals = tiles + (size_t)STAGES * ET * RS;              // STAGES x ET
-    float *fbuf = vals + STAGES * ET;                            // G x 8 x B float4
+    float *fbuf = vals + C::VALS;                                // G x 8 x B float4
     float *rbuf = fbuf + C::FBUF;                                // KP/4 x 32 float4
     __shared__ unsigned next_series;
 
@@ -266,10 +272,23 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
             }
             cp_async_wait<0>();
             flush();   // ends with __syncthreads
-            if (tid < k) A[tid * ld + tid] += lambda;          // trmf.cpp:393
-            block_chol_solve(A, ld, dinv, k);                  // starts and ends with __syncthreads
-            if (tid < k) F[(size_t)j * k + tid] = (float)A[k * ld + tid];
+            if (SOLVE) {
+                if (tid < k) A[tid * ld + tid] += lambda;      // trmf.cpp:393
+                block_chol_solve(A, ld, dinv, k);              // starts and ends with __syncthreads
+                if (tid < k) F[(size_t)j * k + tid] = (float)A[k * ld + tid];
+            } else {
+                float *Gj = Gout + (size_t)j * k * k;
+                for (int p = tid; p < k * k; p += NT) {
+                    const int r = p / k, c = p - r * k;
+                    Gj[p] = (float)(r >= c ? A[r * ld + c] : A[c * ld + r]);
+                }
+                if (tid < k) F[(size_t)j * k + tid] = (float)A[k * ld + tid];
+            }
 #undef RACC
+        } else if (!SOLVE) {
+            float *Gj = Gout + (size_t)j * k * k;
+            for (int p = tid; p < k * k; p += NT) Gj[p] = 0.f;
+            if (tid < k) F[(size_t)j * k + tid] = 0.f;
         }
         __syncthreads();
         if (tid == 0) next_series = atomicAdd(queue, 1u);
@@ -283,8 +302,9 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
 static inline bool f_update_tiled_supported(int k) { return k >= 4 && k <= 64 && (k % 4) == 0; }
 
 // returns 0 on success
+template <bool SOLVE>
 static inline int f_update_tiled_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
-                                        const V *X, V *F, int k, double lambda, uint32_t nseries, unsigned *queue,
+                                        const V *X, V *F, V *Gout, int k, double lambda, uint32_t nseries, unsigned *queue,
                                         unsigned long long *launches) {
     const int NB = (k + 7) / 8;
     const unsigned grid = (unsigned)(nseries < (uint32_t)(2 * num_sms) ? nseries : (uint32_t)(2 * num_sms));
@@ -292,8 +312,9 @@ static inline int f_update_tiled_launch(cudaStream_t st, int num_sms, const uint
 #define FT_CASE(N)                                                                                              \
     case N: {                                                                                                   \
         const size_t smem = ft::smem_bytes<N>(k);                                                               \
-        if (cudaFuncSetAttribute(ft::f_update_tiled_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-        ft::f_update_tiled_kernel<N><<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, k, lambda, nseries, queue); \
+        auto kfn = ft::f_update_tiled_kernel<N, SOLVE>;                                                         \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+        kfn<<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, Gout, k, lambda, nseries, queue);       \
         break;                                                                                                  \
     }
     switch (NB) {
@@ -308,6 +329,7 @@ static inline int f_update_tiled_launch(cudaStream_t st, int num_sms, const uint
 #else   // float64 build: the generic kernel (fp64 FMAs) is the parity path
 
 static inline bool f_update_tiled_supported(int) { return false; }
-static inline int f_update_tiled_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, V *, int,
+template <bool SOLVE>
+static inline int f_update_tiled_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, V *, V *, int,
                                         double, uint32_t, unsigned *, unsigned long long *) { return 1; }
 #endif

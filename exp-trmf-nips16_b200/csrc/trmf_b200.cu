@@ -101,6 +101,9 @@ struct trmf_b200_session {
     void *nccl_comm = nullptr;
     bool own_comm = false;
     V *part_tk = nullptr;         // this rank's partial of a T x k pass, all-reduced in place
+    // X-update through per-time-stamp Grams (fp32 build, k % 4 == 0, k <= 64)
+    V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
+    int gram_state = 0;               // 0 = not decided, 1 = enabled, -1 = disabled
     unsigned long long collectives = 0;
 
     double lambdaI = 0.1, lambdaAR = 0.1, lambdaLag = 0.1;
@@ -220,6 +223,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     cudaFree(s->part_tk);
+    cudaFree(s->Gt); cudaFree(s->bt);
     if (s->own_Y) {
         cudaFree(s->row_ptr); cudaFree(s->col_ptr); cudaFree(s->col_idx); cudaFree(s->row_idx);
         cudaFree(s->val_t); cudaFree(s->val); cudaFree(s->Yd);
@@ -480,6 +484,61 @@ static int hv_launch(S *s, const V *d, V *Hd) {
     return gemm<V, double, V>(s, d, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, Hd, 1.0, 0.0, Hd);
 }
 
+// fun(w) and grad(w) at the same point from one walk over Omega (rf_tron.h:154-158 evaluates both
+// at w before the CG solve): base value + base gradient share rho, loss value + loss gradient
+// share the residuals.
+static int fun_grad_launch(S *s, const V *w, V *g) {
+    const size_t tk = s->T * (size_t)s->k;
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, s->T, s->k);
+    LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, w, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
+    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, g, s->T, s->k, s->lambdaI, s->lambdaAR);
+    if (s->world == 1) {
+        if (sparse_pass<MODE_GRADFUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, w, g, s->T, SC_FLOSS, true)) return 1;
+    } else {
+        if (sparse_pass<MODE_GRADFUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, w, s->part_tk, s->T, SC_FLOSS, false)) return 1;
+        if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
+        if (dist_allreduce_f64(s, s->scal + SC_FLOSS, 1)) return 1;
+        LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, g, 1.0, s->part_tk, 0.0, (const V *)nullptr, g, tk);
+    }
+    return 0;
+}
+
+// Decide once per session whether the CG Hessian-vector products go through per-time-stamp
+// Grams (needs T*k*k values of HBM; fp32 build with a tiled-kernel-compatible k).
+static int gram_prepare(S *s) {
+    if (s->gram_state != 0) return 0;
+    s->gram_state = -1;
+    if (!s->missing || !f_update_tiled_supported(s->k) || getenv("TRMF_B200_NO_GRAM_HV")) return 0;
+    if ((((uintptr_t)s->H) & 15) != 0) return 0;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    const size_t need = (s->T * (size_t)s->k * s->k + s->T * (size_t)s->k) * sizeof(V);
+    if (need > free_b / 2) return 0;
+    if (dev_alloc(&s->Gt, s->T * (size_t)s->k * s->k) || dev_alloc(&s->bt, s->T * (size_t)s->k)) return 1;
+    s->gram_state = 1;
+    return 0;
+}
+
+static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd) {
+    const int k = s->k;
+    const int WARPS = 8;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((s->T + WARPS - 1) / WARPS, (size_t)s->num_sms * 8));
+    const size_t tk = s->T * (size_t)k;
+    if (base_apply(s, d, Hd)) return 1;
+    if (s->world == 1) {
+        double *dhd = want_dhd ? s->scal + SC_DHD : nullptr;
+        if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, d, Hd, k, s->T, true, s->part, s->ticket, dhd);
+        else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, d, Hd, k, s->T, true, s->part, s->ticket, dhd);
+    } else {
+        if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, d, s->part_tk, k, s->T, false, s->part, s->ticket, (double *)nullptr);
+        else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, d, s->part_tk, k, s->T, false, s->part, s->ticket, (double *)nullptr);
+        if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
+        LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, Hd, 1.0, s->part_tk, 0.0, (const V *)nullptr, Hd, tk);
+        if (want_dhd && dot(s, d, Hd, tk, SC_DHD)) return 1;
+    }
+    return 0;
+}
+
 // --------------------------------------------------------------------------
 // the three phases
 // --------------------------------------------------------------------------
@@ -491,8 +550,8 @@ extern "C" int trmf_b200_f_update(S *s) {
     if (s->missing) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
         if (f_update_tiled_supported(k) && (((uintptr_t)s->W) & 15) == 0 && !getenv("TRMF_B200_GENERIC_F")) {
-            if (f_update_tiled_launch(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, k, s->lambdaI,
-                                      (uint32_t)s->n, s->ticket + 1, &s->launches))
+            if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
+                                            s->lambdaI, (uint32_t)s->n, s->ticket + 1, &s->launches))
                 return fail("f_update_tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             const int ENT = 32;
@@ -551,13 +610,22 @@ extern "C" int trmf_b200_x_update(S *s) {
     const size_t max_cg = std::min<size_t>(20, tk);
 
     if (!s->missing && dense_loss_init(s)) return 1;   // fun_obj->init(), trmf.h:166-173
-    if (fun_launch(s, s->W)) return 1;
-    if (read_scalars(s)) return 1;                     // (the grad below does not depend on it; cheap)
-    const double f = fun_combine(s);
-    if (grad_launch(s, s->W, s->g)) return 1;
     int cur = SC_RTR, nxt = SC_RNEW;
+    if (s->missing) {
+        if (gram_prepare(s)) return 1;
+        if (s->gram_state == 1) {   // Grams of the (fixed) series factor over every time stamp's observed set
+            if (f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
+                                             (uint32_t)s->T, s->ticket + 1, &s->launches))
+                return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (fun_grad_launch(s, s->W, s->g)) return 1;
+    } else {
+        if (fun_launch(s, s->W)) return 1;
+        if (grad_launch(s, s->W, s->g)) return 1;
+    }
     LAUNCH(s, cg_init_kernel, eg, 256, 0, s->g, s->s, s->r, s->d, tk, s->part, s->ticket, s->scal + cur);
     if (read_scalars(s)) return 1;
+    const double f = fun_combine(s);
     const double gg = s->h_scal[cur];
     const double gnorm = std::sqrt(gg);
     s->st_f = f; s->st_fnew = f; s->st_gnorm = gnorm; s->st_cg = 0; s->st_acc = 0; s->st_prered = 0; s->st_actred = 0;
@@ -572,8 +640,12 @@ extern "C" int trmf_b200_x_update(S *s) {
             if (rnorm <= cgtol) break;
             if (cg_iter >= max_cg) break;
             ++cg_iter;
-            if (hv_launch(s, s->d, s->Hd)) return 1;
-            if (dot(s, s->d, s->Hd, tk, SC_DHD)) return 1;
+            if (s->missing && s->gram_state == 1) {
+                if (gram_hv_launch(s, s->d, s->Hd, true)) return 1;
+            } else {
+                if (hv_launch(s, s->d, s->Hd)) return 1;
+                if (dot(s, s->d, s->Hd, tk, SC_DHD)) return 1;
+            }
             LAUNCH(s, cg_step1_kernel, eg, 256, 0, s->s, s->r, s->d, s->Hd, tk, s->scal, cur, nxt, s->part, s->ticket);
             LAUNCH(s, cg_step2_kernel, eg, 256, 0, s->d, s->r, tk, s->scal, cur, nxt);
             if (read_scalars(s)) return 1;

@@ -86,7 +86,9 @@ __global__ void base_fun_kernel(const V *__restrict__ S, const double *__restric
 // for entry e; phase B: lane t accumulates column t over the 32 entries.
 // fp32 build: fp32 FMAs within a 32-entry tile, fp64 across tiles.
 // ---------------------------------------------------------------------------
-enum { MODE_FUN = 0, MODE_GRAD = 1, MODE_HV = 2, MODE_SPMM = 3 };
+//   MODE_GRADFUN: MODE_GRAD and MODE_FUN from the same residuals in one pass (fun(w) and grad(w) are
+//                 always evaluated at the same point at the start of the Newton step, rf_tron.h:154-158)
+enum { MODE_FUN = 0, MODE_GRAD = 1, MODE_HV = 2, MODE_SPMM = 3, MODE_GRADFUN = 4 };
 
 template <int MODE, int KR, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
@@ -133,8 +135,8 @@ sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict_
                     const V *hr = tile + lane * ks;
                     for (int t = 0; t < k; ++t) z += svec[t] * hr[t];
                 }
-                if (MODE == MODE_GRAD) z -= y;
-                if (MODE == MODE_FUN) { const double rr = (double)y - (double)z; if (valid) fsum += rr * rr; }
+                if (MODE == MODE_FUN || MODE == MODE_GRADFUN) { const double rr = (double)y - (double)z; if (valid) fsum += rr * rr; }
+                if (MODE == MODE_GRAD || MODE == MODE_GRADFUN) z -= y;
             }
             if (MODE != MODE_FUN) {
                 V accf[KR];
@@ -161,7 +163,7 @@ sparse_pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict_
         }
         __syncwarp();
     }
-    if (MODE == MODE_FUN) {
+    if (MODE == MODE_FUN || MODE == MODE_GRADFUN) {
         double v = block_sum(fsum, red);
         grid_sum_commit(v, part, ticket, fout, 0.5, red);
     }
@@ -267,5 +269,58 @@ __global__ void tron_trial_kernel(const V *__restrict__ w, const V *__restrict__
         va = block_sum(va, red);
         vb = block_sum(vb, red);
         if (threadIdx.x == 0) { *gs_out = va; *sr_out = vb; *ticket = 0u; }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Hessian-vector product of the loss through precomputed per-time-stamp Grams:
+//   (Hv)_i = ( sum_{j in Omega_i} h_j h_j^T ) s_i = G_i s_i        (same map as trmf.cpp:269-288)
+// H is fixed during the X-update, so G_i (k x k, fp32, full symmetric square, built once per
+// X-update by f_update_tiled_kernel<.., SOLVE=false>) turns every CG step from a walk over Omega
+// (N (4+4k) gathered bytes) into a stream over T k^2 floats.  One warp per time stamp; lane t owns
+// output component(s) t, t+32 and walks the rows u of the symmetric G_i, so every load is a
+// coalesced row segment; fp64 accumulation.  out_i = (accum ? out_i : 0) + G_i s_i, and the CG
+// scalar d^T(Hd) is reduced in the same pass (deterministic two-level sum) when dhd != nullptr.
+// ---------------------------------------------------------------------------
+template <int KR, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+gram_matvec_kernel(const V *__restrict__ Gm, const V *__restrict__ S, V *__restrict__ out, int k, size_t T, bool accum,
+                   double *part, unsigned *ticket, double *dhd) {
+    __shared__ double red[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double dsum = 0.0;
+    for (size_t i = (size_t)blockIdx.x * WARPS + wid; i < T; i += (size_t)gridDim.x * WARPS) {
+        const V *Gi = Gm + i * (size_t)k * k;
+        V sv[KR];
+        double acc[KR];
+#pragma unroll
+        for (int q = 0; q < KR; ++q) {
+            const int t = lane + 32 * q;
+            sv[q] = t < k ? S[i * k + t] : (V)0;
+            acc[q] = 0.0;
+        }
+        for (int u = 0; u < k; ++u) {
+            const V su = __shfl_sync(FULL_MASK, sv[u >> 5], u & 31);   // KR <= 2 here: see launcher
+            const V *row = Gi + (size_t)u * k;
+#pragma unroll
+            for (int q = 0; q < KR; ++q) {
+                const int t = lane + 32 * q;
+                if (t < k) acc[q] += (double)row[t] * (double)su;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KR; ++q) {
+            const int t = lane + 32 * q;
+            if (t < k) {
+                const double o = (accum ? (double)out[i * k + t] : 0.0) + acc[q];
+                const V ov = (V)o;
+                out[i * k + t] = ov;
+                dsum += (double)sv[q] * (double)ov;
+            }
+        }
+    }
+    if (dhd != nullptr) {
+        double v = block_sum(dsum, red);
+        grid_sum_commit(v, part, ticket, dhd, 1.0, red);
     }
 }
