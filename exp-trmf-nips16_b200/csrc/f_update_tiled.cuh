@@ -3,17 +3,21 @@
 //
 // Replaces the hot loop of l2r_ls_pY_IX_chol::solve (reference trmf.cpp:382-395): per
 // observed entry the reference does k(k+1)/2 + k scalar multiply-adds into a k x k buffer.
-// Here one CTA (8 "Gram" warps + 1 "rhs" warp) owns one series at a time:
+// Here one CTA (7 "Gram" warps + 1 "rhs" warp) owns one series at a time:
 //
 //  * the observed rows x_i (k floats each, gathered through the by-series index list)
-//    are staged into shared memory by cp.async (16 B per request, no register
-//    staging), 3 stages deep, one __syncthreads per tile; the index stream is
-//    prefetched into registers one tile ahead so the gather never waits on it;
+//    are staged into shared memory by cp.async (LDGSTS, 16 B per request, no register
+//    staging): a lane owns a fixed (row-in-instruction, chunk) slot and a warp every 8th
+//    warp-wide request of a tile, the row indices are prefetched into registers one tile
+//    ahead, so a request costs ~4 instructions and a warp ~25 per tile; 3 stages deep, one
+//    __syncthreads per tile.  (Measured alternatives that lost: all copies from the light
+//    warp -- it becomes the straggler at the barrier; per-stage mbarriers instead of the
+//    barrier -- the spin loops eat the issue slots; TMA row copies -- see below.)
 //  * the k indices are split into NB = KP/8 sets R(t) of 8 (two 16-byte chunks, t and
 //    t+NB, so that lanes of a group read distinct bank groups); the upper triangle of
 //    the Gram is the B = NB(NB+1)/2 blocks R(bi) x R(bj), bi <= bj; a Gram thread is
 //    (group g, block b): it keeps the 8x8 block in 64 fp32 registers and, per entry,
-//    loads 4 x LDS.128 and issues 64 FFMA.  G = 256/B groups work on different entries
+//    loads 4 x LDS.128 and issues 64 FFMA.  G = 224/B groups work on different entries
 //    of the same tile, so a fp32 partial sum never covers more than 128 entries;
 //  * every FL tiles the G partial blocks are reduced through shared memory into ONE
 //    fp64 Gram per CTA (each matrix element has a single owner thread: no atomics,
@@ -31,40 +35,56 @@
 
 namespace ft {
 
-constexpr int NT = 288;       // 8 Gram warps + 1 rhs warp
-constexpr int NGRAM = 256;
+// 7 Gram warps + 1 rhs warp.  8 warps x 128 registers lets two CTAs share an SM (the register
+// file is handed out in pairs of warps, so a 9-warp CTA is billed as 10 and drops to 1 CTA/SM).
+constexpr int NT = 256;
+constexpr int NGRAM = 224;
 
-template <int NB> struct Cfg {
+template <int K> struct Cfg {
+    static constexpr int NB = (K + 7) / 8;
     static constexpr int KP = 8 * NB;
+    static constexpr int CH = K / 4;           // 16-byte chunks per factor row
     static constexpr int B = NB * (NB + 1) / 2;
     static constexpr int G = NGRAM / B;
-    static constexpr int U = NB == 1 ? 1 : NB == 2 ? 2 : NB == 3 ? 3 : NB == 4 ? 5 : NB == 5 ? 6 : NB == 8 ? 6 : 8;
+    static constexpr int U = NB == 1 ? 1 : NB == 2 ? 2 : NB == 3 ? 3 : NB == 4 ? 5 : NB == 5 ? 7 : 8;
     static constexpr int ET = G * U;           // entries per tile
     static constexpr int RS = KP + 4;          // smem row stride (floats): odd number of 16-B chunks
     static constexpr int STAGES = 3;
     static constexpr int FL = (128 / U) > 0 ? (128 / U) : 1;   // tiles between fp32 -> fp64 flushes
     static constexpr int FBUF = G * B * 32;    // floats: half of every lane's 8x8 block
     static constexpr int RBUF = 32 * KP;       // floats: rhs partials of the 32 rhs lanes
-    static constexpr int VALS = (STAGES * ET + 3) / 4 * 4;   // staged Y values, padded so fbuf stays 16-B aligned
+    static constexpr int NQ = (ET + 31) / 32;  // rows per rhs lane per tile
+    // group g works on tile rows u*G + (g*D mod G): neighbouring groups sit D rows apart, which
+    // keeps quarter-warps that straddle two groups off the same shared-memory banks
+    static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
+    static constexpr int pick_d_() {
+        for (int d = 1; d < G; ++d) {
+            const int shift = (d * (RS / 4)) % 8;   // bank-group offset between neighbouring groups' rows
+            if (gcd_(d, G) == 1 && shift >= 5) return d;
+        }
+        return 1;
+    }
+    static constexpr int D = pick_d_();
 };
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+// ---- cp.async (LDGSTS) primitives ----
+// (A TMA variant -- one cp.async.bulk per gathered 160-byte row, mbarrier completion -- was
+//  measured 3x slower end to end: per-row bulk requests are far too small for the copy engine.)
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pred) {
     const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *smem, const void *gmem) {
-    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %2, 0;\n\t@p cp.async.cg.shared.global [%0], [%1], 16;\n\t}"
+                 ::"r"(s), "l"(gmem), "r"((int)pred) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NB>
-static size_t smem_bytes(int k) {
-    typedef Cfg<NB> C;
+template <int K>
+static size_t smem_bytes() {
+    typedef Cfg<K> C;
+    const int k = K;
     size_t dbl = (size_t)(k + 1) * (k + 1) + k;
     dbl = (dbl + 1) & ~(size_t)1;   // keep the float region 16-B aligned
-    return dbl * sizeof(double) + sizeof(float) * ((size_t)C::STAGES * C::ET * C::RS + C::VALS + C::FBUF + C::RBUF);
+    return dbl * sizeof(double) + sizeof(float) * ((size_t)C::STAGES * C::ET * C::RS + C::FBUF + C::RBUF);
 }
 
 // index of member m (0..7) of set R(t): chunk t then chunk t + NB
@@ -75,58 +95,62 @@ template <int NB> __device__ __forceinline__ int set_index(int t, int m) { retur
 //                the k x k Gram (full symmetric square, fp32) goes to Gout[j] and the rhs to
 //                F[j]; rows without entries get zeros.  The Hessian-vector products of the CG
 //                solve then read these Grams instead of re-walking Omega (x_update.cuh).
-template <int NB, bool SOLVE>
+template <int K, bool SOLVE>
 __global__ void __launch_bounds__(NT, 2)
 f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
-                      const float *__restrict__ X, float *__restrict__ F, float *__restrict__ Gout, int k, double lambda,
+                      const float *__restrict__ X, float *__restrict__ F, float *__restrict__ Gout, double lambda,
                       uint32_t nseries, unsigned *__restrict__ queue) {
-    typedef Cfg<NB> C;
-    constexpr int KP = C::KP, B = C::B, G = C::G, U = C::U, ET = C::ET, RS = C::RS, STAGES = C::STAGES;
+    typedef Cfg<K> C;
+    constexpr int k = K, NB = C::NB, CH = C::CH;
+    constexpr int KP = C::KP, B = C::B, G = C::G, U = C::U, ET = C::ET, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
+    constexpr int RPI = 32 / CH;                    // factor rows moved by one warp-wide LDGSTS
+    constexpr int NCI = (ET + RPI - 1) / RPI;       // warp-wide LDGSTS instructions per tile
+    constexpr int NW = NT / 32;
+    constexpr int NI = (NCI + NW - 1) / NW;         // ... of which every warp issues NI (instruction q = warp + NW*i)
+    constexpr int STAGE_FLOATS = ET * RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int ld = k + 1;
+    constexpr int ld = k + 1;
     double *A = reinterpret_cast<double *>(smem_raw);            // (k+1) x ld: lower triangle + rhs row
     double *dinv = A + (size_t)(k + 1) * ld;
-    size_t dbl = (size_t)(k + 1) * ld + k;
-    dbl = (dbl + 1) & ~(size_t)1;
+    constexpr size_t dbl = (((size_t)(k + 1) * ld + k) + 1) & ~(size_t)1;
     float *tiles = reinterpret_cast<float *>(A + dbl);           // STAGES x ET x RS
-    float *vals = tiles + (size_t)STAGES * ET * RS;              // STAGES x ET
-    float *fbuf = vals + C::VALS;                                // G x 8 x B float4
+    float *fbuf = tiles + (size_t)STAGES * STAGE_FLOATS;         // G x 8 x B float4
     float *rbuf = fbuf + C::FBUF;                                // KP/4 x 32 float4
     __shared__ unsigned next_series;
 
     const int tid = threadIdx.x;
-    const int CH = k >> 2;                                       // 16-byte chunks per factor row (k % 4 == 0)
     const bool is_gram = tid < NGRAM;
     const int g = tid / B, b = tid - g * B;
     const bool active = is_gram && g < G;
-    int bi = 0;
+    int bi = 0, bj = 0;
     {
         int rem = b;
         while (rem >= NB - bi) { rem -= NB - bi; ++bi; }
-        // bj = bi + rem
-    }
-    int bj;
-    {
-        int rem = b, t = 0;
-        while (rem >= NB - t) { rem -= NB - t; ++t; }
-        bj = t + rem;
+        bj = bi + rem;
     }
     const int lane = tid & 31;
+    const int grow = (g * C::D) % G;                 // this group's row inside every G-row slice of a tile
+    // Gram thread: offsets of its a- and b-operands inside a stage
+    const int off_a = grow * RS + 4 * bi, off_b = grow * RS + 4 * bj;
+    // copy duty, shared by all 8 warps: lane -> (row within an LDGSTS instruction, 16-byte chunk of that row)
+    const int warp = tid >> 5;
+    const int cp_r = lane / CH, cp_c = lane - cp_r * CH;
+    const bool cp_on = lane < RPI * CH;
+    const float *cp_src = X + cp_c * 4;
+    const int cp_dst = cp_r * RS + cp_c * 4;
 
     // zero every staging row once: padding columns (k..KP+3) are never written by the copies
-    for (int p = tid; p < STAGES * ET * RS; p += NT) tiles[p] = 0.f;
-
-    constexpr int NCOPY = (ET * (KP / 4) + NT - 1) / NT;
-    uint32_t nidx[NCOPY];
-
+    for (int p = tid; p < STAGES * STAGE_FLOATS; p += NT) tiles[p] = 0.f;
     if (tid == 0) next_series = atomicAdd(queue, 1u);
     __syncthreads();
     uint32_t j = next_series;
 
     while (j < nseries) {
-        const uint64_t lo = ptr[j], hi = ptr[j + 1];
-        const uint64_t nnz = hi - lo;
+        const uint64_t lo = ptr[j];
+        const uint32_t nnz = (uint32_t)(ptr[j + 1] - lo);       // one series never holds 2^32 entries (T < 2^32)
         if (nnz != 0) {
+            const uint32_t *sidx = idx + lo;
+            const float *sval = val + lo;
             const int ntiles = (int)((nnz + ET - 1) / ET);
             for (int p = tid; p < (k + 1) * ld; p += NT) A[p] = 0.0;
 
@@ -138,36 +162,39 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
             // the rhs warp keeps its KP partial sums in the same registers: racc[t] == acc[t >> 3][t & 7]
 #define RACC(t) acc[(t) >> 3][(t) & 7]
 
+            uint32_t nidx[NI];            // row indices of this thread's copy slots in the next tile to issue
+            float vcur[NQ], vnext[NQ];    // light warp: Y values of the tile being consumed / of the next one
             auto tile_count = [&](int tt) -> int {
-                const uint64_t base = lo + (uint64_t)tt * ET;
-                return (int)((hi - base) < (uint64_t)ET ? (hi - base) : (uint64_t)ET);
+                const uint32_t rem = nnz - (uint32_t)tt * ET;
+                return (int)(rem < (uint32_t)ET ? rem : (uint32_t)ET);
             };
             auto load_idx = [&](int tt) {
-                const uint64_t base = lo + (uint64_t)tt * ET;
-                const int ncp = tile_count(tt) * CH;
+                const uint32_t base = (uint32_t)tt * ET;
+                const int cnt = tile_count(tt);
 #pragma unroll
-                for (int q = 0; q < NCOPY; ++q) {
-                    const int c = tid + q * NT;
-                    nidx[q] = c < ncp ? __ldg(idx + base + c / CH) : 0u;
+                for (int i = 0; i < NI; ++i) {
+                    const int e = RPI * (warp + NW * i) + cp_r;
+                    nidx[i] = (cp_on && e < cnt) ? __ldg(sidx + base + e) : 0u;
                 }
             };
-            auto issue = [&](int tt) {   // uses nidx loaded for tile tt
-                const int stage = tt % STAGES;
-                const uint64_t base = lo + (uint64_t)tt * ET;
-                const int cnt = tile_count(tt);
-                const int ncp = cnt * CH;
-                float *dst = tiles + (size_t)stage * ET * RS;
+            auto load_vals = [&](int tt) {
+                const uint32_t base = (uint32_t)tt * ET;
 #pragma unroll
-                for (int q = 0; q < NCOPY; ++q) {
-                    const int c = tid + q * NT;
-                    if (c < ncp) {
-                        const int e = c / CH, ch = c - e * CH;
-                        cp_async16(dst + e * RS + ch * 4, X + (size_t)nidx[q] * k + ch * 4);
-                    }
+                for (int q = 0; q < NQ; ++q) {
+                    const uint32_t e = base + lane + 32 * q;
+                    vnext[q] = (lane + 32 * q < ET && e < nnz) ? __ldg(sval + e) : 0.f;
                 }
-                for (int e = tid; e < cnt; e += NT) cp_async4(vals + stage * ET + e, val + base + e);
+            };
+            auto issue = [&](int tt, int stage) {   // gathers this thread's slots of tile tt (indices in nidx) into `stage`
+                float *dst = tiles + stage * STAGE_FLOATS + cp_dst + warp * (RPI * RS);
+                const int cnt = tile_count(tt);
+#pragma unroll
+                for (int i = 0; i < NI; ++i) {
+                    const int e = RPI * (warp + NW * i) + cp_r;
+                    cp_async16(dst + i * (NW * RPI * RS), cp_src + (size_t)nidx[i] * k, cp_on && e < cnt);
+                }
                 if (cnt < ET)   // tail tile: stale rows from an earlier tile must read as zero
-                    for (int p = cnt * RS + tid; p < ET * RS; p += NT) dst[p] = 0.f;
+                    for (int p = cnt * RS + tid; p < STAGE_FLOATS; p += NT) tiles[stage * STAGE_FLOATS + p] = 0.f;
             };
             auto flush = [&]() {
 #pragma unroll
@@ -220,54 +247,67 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                     for (int jj = 0; jj < 8; ++jj) acc[i][jj] = 0.f;
             };
 
-            // ---- pipeline prologue: tiles 0 .. STAGES-2 in flight, indices of tile STAGES-1 in registers ----
+            // ---- pipeline prologue: tiles 0 .. STAGES-2 in flight, indices of tile STAGES-1 loaded ----
 #pragma unroll
             for (int s = 0; s < STAGES - 1; ++s) {
-                if (s < ntiles) { load_idx(s); issue(s); }
+                if (s < ntiles) { load_idx(s); issue(s, s); }
                 cp_async_commit();
             }
             if (STAGES - 1 < ntiles) load_idx(STAGES - 1);
+            if (!is_gram) load_vals(0);
 
+            int stage = 0;                         // stage holding tile t
             for (int t = 0; t < ntiles; ++t) {
-                cp_async_wait<STAGES - 2>();
-                __syncthreads();   // tile t landed for everyone; everyone is done with tile t-1
-                if (t + STAGES - 1 < ntiles) issue(t + STAGES - 1);
-                cp_async_commit();
-                if (t + STAGES < ntiles) load_idx(t + STAGES);
-
-                const float *tb = tiles + (size_t)(t % STAGES) * ET * RS;
-                if (active) {
-                    const float *pa = tb + 4 * bi, *pb = tb + 4 * bj;
+                cp_async_wait<STAGES - 2>();       // my share of tile t has landed
+                __syncthreads();                   // ... and everybody else's; tile t-1 is fully consumed
+                {
+                    const int nt = t + STAGES - 1;
+                    int ns = stage + STAGES - 1;
+                    if (ns >= STAGES) ns -= STAGES;
+                    if (nt < ntiles) issue(nt, ns);
+                    cp_async_commit();
+                    if (nt + 1 < ntiles) load_idx(nt + 1);
+                }
+                if (is_gram) {
+                    if (active) {
+                        const float *pa = tiles + stage * STAGE_FLOATS + off_a, *pb = tiles + stage * STAGE_FLOATS + off_b;
 #pragma unroll
-                    for (int u = 0; u < U; ++u) {
-                        const int e = g + u * G;
-                        const float4 a0 = *reinterpret_cast<const float4 *>(pa + e * RS);
-                        const float4 a1 = *reinterpret_cast<const float4 *>(pa + e * RS + 4 * NB);
-                        const float4 b0 = *reinterpret_cast<const float4 *>(pb + e * RS);
-                        const float4 b1 = *reinterpret_cast<const float4 *>(pb + e * RS + 4 * NB);
-                        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                        const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        for (int u = 0; u < U; ++u) {
+                            const float4 a0 = *reinterpret_cast<const float4 *>(pa + u * G * RS);
+                            const float4 a1 = *reinterpret_cast<const float4 *>(pa + u * G * RS + 4 * NB);
+                            const float4 b0 = *reinterpret_cast<const float4 *>(pb + u * G * RS);
+                            const float4 b1 = *reinterpret_cast<const float4 *>(pb + u * G * RS + 4 * NB);
+                            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+                            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-                        for (int i = 0; i < 8; ++i)
+                            for (int i = 0; i < 8; ++i)
 #pragma unroll
-                            for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(a[i], bv[jj], acc[i][jj]);
+                                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(a[i], bv[jj], acc[i][jj]);
+                        }
                     }
-                } else if (!is_gram) {
-                    const int cnt = tile_count(t);
-                    const float *tv = vals + (t % STAGES) * ET;
-                    for (int e = lane; e < cnt; e += 32) {
-                        const float y = tv[e];
-                        const float *row = tb + e * RS;
+                } else {
 #pragma unroll
-                        for (int c4 = 0; c4 < KP / 4; ++c4) {
-                            const float4 w = *reinterpret_cast<const float4 *>(row + 4 * c4);
-                            RACC(4 * c4 + 0) = fmaf(y, w.x, RACC(4 * c4 + 0));
-                            RACC(4 * c4 + 1) = fmaf(y, w.y, RACC(4 * c4 + 1));
-                            RACC(4 * c4 + 2) = fmaf(y, w.z, RACC(4 * c4 + 2));
-                            RACC(4 * c4 + 3) = fmaf(y, w.w, RACC(4 * c4 + 3));
+                    for (int q = 0; q < NQ; ++q) vcur[q] = vnext[q];
+                    if (t + 1 < ntiles) load_vals(t + 1);
+                    const float *tb = tiles + stage * STAGE_FLOATS;
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q) {
+                        const int e = lane + 32 * q;     // rows past the tile's count are zero and carry y = 0
+                        if (e < ET) {
+                            const float y = vcur[q];
+                            const float *row = tb + e * RS;
+#pragma unroll
+                            for (int c4 = 0; c4 < KP / 4; ++c4) {
+                                const float4 w = *reinterpret_cast<const float4 *>(row + 4 * c4);
+                                RACC(4 * c4 + 0) = fmaf(y, w.x, RACC(4 * c4 + 0));
+                                RACC(4 * c4 + 1) = fmaf(y, w.y, RACC(4 * c4 + 1));
+                                RACC(4 * c4 + 2) = fmaf(y, w.z, RACC(4 * c4 + 2));
+                                RACC(4 * c4 + 3) = fmaf(y, w.w, RACC(4 * c4 + 3));
+                            }
                         }
                     }
                 }
+                if (++stage == STAGES) stage = 0;
                 if ((t + 1) % C::FL == 0 && t + 1 < ntiles) flush();
             }
             cp_async_wait<0>();
@@ -299,26 +339,28 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
 
 }   // namespace ft
 
-static inline bool f_update_tiled_supported(int k) { return k >= 4 && k <= 64 && (k % 4) == 0; }
+static inline bool f_update_tiled_supported(int k) {
+    switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: case 56: case 60: case 64: return true; }
+    return false;
+}
 
 // returns 0 on success
 template <bool SOLVE>
 static inline int f_update_tiled_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
                                         const V *X, V *F, V *Gout, int k, double lambda, uint32_t nseries, unsigned *queue,
                                         unsigned long long *launches) {
-    const int NB = (k + 7) / 8;
     const unsigned grid = (unsigned)(nseries < (uint32_t)(2 * num_sms) ? nseries : (uint32_t)(2 * num_sms));
     if (cudaMemsetAsync(queue, 0, sizeof(unsigned), st) != cudaSuccess) return 1;
-#define FT_CASE(N)                                                                                              \
-    case N: {                                                                                                   \
-        const size_t smem = ft::smem_bytes<N>(k);                                                               \
-        auto kfn = ft::f_update_tiled_kernel<N, SOLVE>;                                                         \
+#define FT_CASE(KK)                                                                                             \
+    case KK: {                                                                                                  \
+        const size_t smem = ft::smem_bytes<KK>();                                                               \
+        auto kfn = ft::f_update_tiled_kernel<KK, SOLVE>;                                                        \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-        kfn<<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, Gout, k, lambda, nseries, queue);       \
+        kfn<<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, Gout, lambda, nseries, queue);          \
         break;                                                                                                  \
     }
-    switch (NB) {
-        FT_CASE(1) FT_CASE(2) FT_CASE(3) FT_CASE(4) FT_CASE(5) FT_CASE(6) FT_CASE(7) FT_CASE(8)
+    switch (k) {
+        FT_CASE(8) FT_CASE(16) FT_CASE(20) FT_CASE(24) FT_CASE(32) FT_CASE(40) FT_CASE(48) FT_CASE(56) FT_CASE(60) FT_CASE(64)
         default: return 1;
     }
 #undef FT_CASE
