@@ -35,10 +35,13 @@
 
 namespace ft {
 
-// 7 Gram warps + 1 rhs warp.  8 warps x 128 registers lets two CTAs share an SM (the register
-// file is handed out in pairs of warps, so a 9-warp CTA is billed as 10 and drops to 1 CTA/SM).
+// One CTA = 8 warps x 128 registers, two CTAs per SM (the register file is handed out in pairs of
+// warps: a 9-warp CTA is billed as 10 and drops to one CTA/SM -- measured).  Roles: 6 "Gram" warps,
+// one producer warp (all cp.async traffic) and one rhs warp.  Which warp ids play which role depends
+// on the CTA's "flavor" (0 or 1 = arrival order on its SM) so that the two co-resident CTAs together
+// put exactly 3 Gram warps + 1 light warp on each of the SM's 4 schedulers (warp id % 4).
 constexpr int NT = 256;
-constexpr int NGRAM = 224;
+constexpr int NGRAM = 192;
 
 template <int K> struct Cfg {
     static constexpr int NB = (K + 7) / 8;
@@ -46,14 +49,16 @@ template <int K> struct Cfg {
     static constexpr int CH = K / 4;           // 16-byte chunks per factor row
     static constexpr int B = NB * (NB + 1) / 2;
     static constexpr int G = NGRAM / B;
-    static constexpr int U = NB == 1 ? 1 : NB == 2 ? 2 : NB == 3 ? 3 : NB == 4 ? 5 : NB == 5 ? 7 : 8;
+    static constexpr int U = NB == 1 ? 1 : NB == 2 ? 2 : NB == 3 ? 3 : NB == 4 ? 5 : NB == 5 ? 8 : NB == 6 ? 10 : NB == 7 ? 12 : 10;
     static constexpr int ET = G * U;           // entries per tile
     static constexpr int RS = KP + 4;          // smem row stride (floats): odd number of 16-B chunks
     static constexpr int STAGES = 3;
     static constexpr int FL = (128 / U) > 0 ? (128 / U) : 1;   // tiles between fp32 -> fp64 flushes
     static constexpr int FBUF = G * B * 32;    // floats: half of every lane's 8x8 block
     static constexpr int RBUF = 32 * KP;       // floats: rhs partials of the 32 rhs lanes
-    static constexpr int NQ = (ET + 31) / 32;  // rows per rhs lane per tile
+    static constexpr int NQ = (ET + 31) / 32;  // tile rows per lane of a light warp
+    static constexpr int RPI = 32 / CH;        // factor rows moved by one warp-wide LDGSTS
+    static constexpr int NCI = (ET + RPI - 1) / RPI;   // warp-wide LDGSTS instructions per tile
     // group g works on tile rows u*G + (g*D mod G): neighbouring groups sit D rows apart, which
     // keeps quarter-warps that straddle two groups off the same shared-memory banks
     static constexpr int gcd_(int a, int b) { return b == 0 ? a : gcd_(b, a % b); }
@@ -99,14 +104,11 @@ template <int K, bool SOLVE>
 __global__ void __launch_bounds__(NT, 2)
 f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
                       const float *__restrict__ X, float *__restrict__ F, float *__restrict__ Gout, double lambda,
-                      uint32_t nseries, unsigned *__restrict__ queue) {
+                      uint32_t nseries, unsigned *__restrict__ queue, unsigned *__restrict__ sm_slots) {
     typedef Cfg<K> C;
     constexpr int k = K, NB = C::NB, CH = C::CH;
     constexpr int KP = C::KP, B = C::B, G = C::G, U = C::U, ET = C::ET, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
-    constexpr int RPI = 32 / CH;                    // factor rows moved by one warp-wide LDGSTS
-    constexpr int NCI = (ET + RPI - 1) / RPI;       // warp-wide LDGSTS instructions per tile
-    constexpr int NW = NT / 32;
-    constexpr int NI = (NCI + NW - 1) / NW;         // ... of which every warp issues NI (instruction q = warp + NW*i)
+    constexpr int RPI = C::RPI, NCI = C::NCI;
     constexpr int STAGE_FLOATS = ET * RS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int ld = k + 1;
@@ -117,10 +119,32 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
     float *fbuf = tiles + (size_t)STAGES * STAGE_FLOATS;         // G x 8 x B float4
     float *rbuf = fbuf + C::FBUF;                                // KP/4 x 32 float4
     __shared__ unsigned next_series;
+    __shared__ unsigned flavor_s;
 
     const int tid = threadIdx.x;
-    const bool is_gram = tid < NGRAM;
-    const int g = tid / B, b = tid - g * B;
+    const int lane = tid & 31, warp = tid >> 5;
+
+    // zero every staging row once: padding columns (k..KP+3) are never written by the copies
+    for (int p = tid; p < STAGES * STAGE_FLOATS; p += NT) tiles[p] = 0.f;
+    if (tid == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        flavor_s = atomicAdd(sm_slots + smid, 1u) & 1u;
+        next_series = atomicAdd(queue, 1u);
+    }
+    __syncthreads();
+    uint32_t j = next_series;
+
+    // ---- roles ----
+    // flavor 0: Gram warps 0,1,2,3,4,5   producer 6   rhs 7     (Gram per scheduler 2,2,1,1)
+    // flavor 1: Gram warps 0,1,2,3,6,7   producer 4   rhs 5     (Gram per scheduler 1,1,2,2)
+    const unsigned flavor = flavor_s;
+    const int w_prod = flavor ? 4 : 6, w_rhs = flavor ? 5 : 7;
+    const bool is_prod = warp == w_prod, is_rhs = warp == w_rhs;
+    const bool is_gram = !is_prod && !is_rhs;
+    const int gw = warp < 4 ? warp : (flavor ? warp - 2 : warp);          // ordinal among the Gram warps (0..5)
+    const int gtid = gw * 32 + lane;
+    const int g = gtid / B, b = gtid - g * B;
     const bool active = is_gram && g < G;
     int bi = 0, bj = 0;
     {
@@ -128,22 +152,13 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
         while (rem >= NB - bi) { rem -= NB - bi; ++bi; }
         bj = bi + rem;
     }
-    const int lane = tid & 31;
     const int grow = (g * C::D) % G;                 // this group's row inside every G-row slice of a tile
-    // Gram thread: offsets of its a- and b-operands inside a stage
     const int off_a = grow * RS + 4 * bi, off_b = grow * RS + 4 * bj;
-    // copy duty, shared by all 8 warps: lane -> (row within an LDGSTS instruction, 16-byte chunk of that row)
-    const int warp = tid >> 5;
+    // producer lane -> (row within a warp-wide LDGSTS, 16-byte chunk of that row)
     const int cp_r = lane / CH, cp_c = lane - cp_r * CH;
     const bool cp_on = lane < RPI * CH;
     const float *cp_src = X + cp_c * 4;
     const int cp_dst = cp_r * RS + cp_c * 4;
-
-    // zero every staging row once: padding columns (k..KP+3) are never written by the copies
-    for (int p = tid; p < STAGES * STAGE_FLOATS; p += NT) tiles[p] = 0.f;
-    if (tid == 0) next_series = atomicAdd(queue, 1u);
-    __syncthreads();
-    uint32_t j = next_series;
 
     while (j < nseries) {
         const uint64_t lo = ptr[j];
@@ -162,19 +177,20 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
             // the rhs warp keeps its KP partial sums in the same registers: racc[t] == acc[t >> 3][t & 7]
 #define RACC(t) acc[(t) >> 3][(t) & 7]
 
-            uint32_t nidx[NI];            // row indices of this thread's copy slots in the next tile to issue
-            float vcur[NQ], vnext[NQ];    // light warp: Y values of the tile being consumed / of the next one
+            // light-warp state (lane l <-> tile rows l, l+32, ...): producer: row indices of the next tile to
+            // issue; rhs warp: Y values of the tile being consumed and of the next one
+            uint32_t nidx[NQ];
+            float vcur[NQ], vnext[NQ];
             auto tile_count = [&](int tt) -> int {
                 const uint32_t rem = nnz - (uint32_t)tt * ET;
                 return (int)(rem < (uint32_t)ET ? rem : (uint32_t)ET);
             };
             auto load_idx = [&](int tt) {
                 const uint32_t base = (uint32_t)tt * ET;
-                const int cnt = tile_count(tt);
 #pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int e = RPI * (warp + NW * i) + cp_r;
-                    nidx[i] = (cp_on && e < cnt) ? __ldg(sidx + base + e) : 0u;
+                for (int q = 0; q < NQ; ++q) {
+                    const uint32_t e = base + lane + 32 * q;
+                    nidx[q] = (lane + 32 * q < ET && e < nnz) ? __ldg(sidx + e) : 0u;
                 }
             };
             auto load_vals = [&](int tt) {
@@ -185,16 +201,24 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                     vnext[q] = (lane + 32 * q < ET && e < nnz) ? __ldg(sval + e) : 0.f;
                 }
             };
-            auto issue = [&](int tt, int stage) {   // gathers this thread's slots of tile tt (indices in nidx) into `stage`
-                float *dst = tiles + stage * STAGE_FLOATS + cp_dst + warp * (RPI * RS);
+            auto issue = [&](int tt, int stage) {   // producer warp: gathers tile tt (indices in nidx) into `stage`
+                float *dst = tiles + stage * STAGE_FLOATS + cp_dst;
                 const int cnt = tile_count(tt);
 #pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    const int e = RPI * (warp + NW * i) + cp_r;
-                    cp_async16(dst + i * (NW * RPI * RS), cp_src + (size_t)nidx[i] * k, cp_on && e < cnt);
+                for (int q = 0; q < NCI; ++q) {
+                    // rows RPI*q .. RPI*q + RPI-1 of the tile; their indices sit in lane e & 31, register e >> 5
+                    const int e = RPI * q + cp_r;
+                    constexpr int QMAX = NQ - 1;
+                    const int m_lo = (RPI * q) >> 5, m_hi = (RPI * q + RPI - 1) >> 5;
+                    uint32_t row = __shfl_sync(FULL_MASK, nidx[m_lo < QMAX ? m_lo : QMAX], e & 31);
+                    if (m_hi != m_lo && m_hi <= QMAX) {
+                        const uint32_t row2 = __shfl_sync(FULL_MASK, nidx[m_hi <= QMAX ? m_hi : QMAX], e & 31);
+                        row = (e >> 5) == m_hi ? row2 : row;
+                    }
+                    cp_async16(dst + q * RPI * RS, cp_src + (size_t)row * k, cp_on && e < cnt);
                 }
                 if (cnt < ET)   // tail tile: stale rows from an earlier tile must read as zero
-                    for (int p = cnt * RS + tid; p < STAGE_FLOATS; p += NT) tiles[stage * STAGE_FLOATS + p] = 0.f;
+                    for (int p = cnt * RS + lane; p < STAGE_FLOATS; p += 32) tiles[stage * STAGE_FLOATS + p] = 0.f;
             };
             auto flush = [&]() {
 #pragma unroll
@@ -210,7 +234,7 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                                 *reinterpret_cast<float4 *>(fbuf + ((size_t)(g * 8 + s4) * B + b) * 4) = v;
                             }
                     }
-                    if (h == 0 && !is_gram) {
+                    if (h == 0 && is_rhs) {
 #pragma unroll
                         for (int c4 = 0; c4 < KP / 4; ++c4)
                             *reinterpret_cast<float4 *>(rbuf + (c4 * 32 + lane) * 4) =
@@ -248,26 +272,20 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
             };
 
             // ---- pipeline prologue: tiles 0 .. STAGES-2 in flight, indices of tile STAGES-1 loaded ----
+            if (is_prod) {
 #pragma unroll
-            for (int s = 0; s < STAGES - 1; ++s) {
-                if (s < ntiles) { load_idx(s); issue(s, s); }
-                cp_async_commit();
+                for (int s = 0; s < STAGES - 1; ++s) {
+                    if (s < ntiles) { load_idx(s); issue(s, s); }
+                    cp_async_commit();
+                }
+                if (STAGES - 1 < ntiles) load_idx(STAGES - 1);
             }
-            if (STAGES - 1 < ntiles) load_idx(STAGES - 1);
-            if (!is_gram) load_vals(0);
+            if (is_rhs) load_vals(0);
 
             int stage = 0;                         // stage holding tile t
             for (int t = 0; t < ntiles; ++t) {
-                cp_async_wait<STAGES - 2>();       // my share of tile t has landed
-                __syncthreads();                   // ... and everybody else's; tile t-1 is fully consumed
-                {
-                    const int nt = t + STAGES - 1;
-                    int ns = stage + STAGES - 1;
-                    if (ns >= STAGES) ns -= STAGES;
-                    if (nt < ntiles) issue(nt, ns);
-                    cp_async_commit();
-                    if (nt + 1 < ntiles) load_idx(nt + 1);
-                }
+                if (is_prod) cp_async_wait<STAGES - 2>();   // the producer issued every copy of tile t
+                __syncthreads();                   // tile t is visible to everyone; tile t-1 is fully consumed
                 if (is_gram) {
                     if (active) {
                         const float *pa = tiles + stage * STAGE_FLOATS + off_a, *pb = tiles + stage * STAGE_FLOATS + off_b;
@@ -285,6 +303,13 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                                 for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(a[i], bv[jj], acc[i][jj]);
                         }
                     }
+                } else if (is_prod) {
+                    const int nt = t + STAGES - 1;
+                    int ns = stage + STAGES - 1;
+                    if (ns >= STAGES) ns -= STAGES;
+                    if (nt < ntiles) issue(nt, ns);
+                    cp_async_commit();
+                    if (nt + 1 < ntiles) load_idx(nt + 1);
                 } else {
 #pragma unroll
                     for (int q = 0; q < NQ; ++q) vcur[q] = vnext[q];
@@ -310,7 +335,7 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                 if (++stage == STAGES) stage = 0;
                 if ((t + 1) % C::FL == 0 && t + 1 < ntiles) flush();
             }
-            cp_async_wait<0>();
+            if (is_prod) cp_async_wait<0>();
             flush();   // ends with __syncthreads
             if (SOLVE) {
                 if (tid < k) A[tid * ld + tid] += lambda;      // trmf.cpp:393
@@ -349,14 +374,15 @@ template <bool SOLVE>
 static inline int f_update_tiled_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
                                         const V *X, V *F, V *Gout, int k, double lambda, uint32_t nseries, unsigned *queue,
                                         unsigned long long *launches) {
+    // queue[0] = series counter, queue[1 .. 1+num_sms) = per-SM CTA arrival counters (role flavor)
     const unsigned grid = (unsigned)(nseries < (uint32_t)(2 * num_sms) ? nseries : (uint32_t)(2 * num_sms));
-    if (cudaMemsetAsync(queue, 0, sizeof(unsigned), st) != cudaSuccess) return 1;
+    if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (size_t)(1 + num_sms), st) != cudaSuccess) return 1;
 #define FT_CASE(KK)                                                                                             \
     case KK: {                                                                                                  \
         const size_t smem = ft::smem_bytes<KK>();                                                               \
         auto kfn = ft::f_update_tiled_kernel<KK, SOLVE>;                                                        \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
-        kfn<<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, Gout, lambda, nseries, queue);          \
+        kfn<<<grid ? grid : 1, ft::NT, smem, st>>>(ptr, idx, val, X, F, Gout, lambda, nseries, queue, queue + 1); \
         break;                                                                                                  \
     }
     switch (k) {

@@ -83,6 +83,7 @@ struct trmf_b200_session {
     double *rho = nullptr;
     double *scal = nullptr, *part = nullptr;
     unsigned *ticket = nullptr;
+    unsigned *queue = nullptr;    // tiled kernel: [0] series counter, [1..] per-SM CTA arrival counters
     double *h_scal = nullptr;     // pinned mirror of `scal`
 
     // dense-mode work space
@@ -165,7 +166,9 @@ static int session_common_init(S *s) {
     if (dev_alloc(&s->g, tk) || dev_alloc(&s->s, tk) || dev_alloc(&s->r, tk) || dev_alloc(&s->d, tk) ||
         dev_alloc(&s->Hd, tk) || dev_alloc(&s->wnew, tk) || dev_alloc(&s->rho, tk))
         return 1;
-    if (dev_alloc(&s->scal, SC_COUNT) || dev_alloc(&s->part, 8192) || dev_alloc(&s->ticket, 4)) return 1;
+    if (dev_alloc(&s->scal, SC_COUNT) || dev_alloc(&s->part, 8192) || dev_alloc(&s->ticket, 4) ||
+        dev_alloc(&s->queue, 1024))
+        return 1;
     CUDA_TRY(cudaMemsetAsync(s->scal, 0, SC_COUNT * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned), s->stream));
     CUDA_TRY(cudaMallocHost((void **)&s->h_scal, SC_COUNT * sizeof(double)));
@@ -232,7 +235,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     cudaFree(s->lags_dev);
     cudaFree(s->W_sv); cudaFree(s->H_sv); cudaFree(s->th_sv);
     cudaFree(s->g); cudaFree(s->s); cudaFree(s->r); cudaFree(s->d); cudaFree(s->Hd); cudaFree(s->wnew);
-    cudaFree(s->rho); cudaFree(s->scal); cudaFree(s->part); cudaFree(s->ticket);
+    cudaFree(s->rho); cudaFree(s->scal); cudaFree(s->part); cudaFree(s->ticket); cudaFree(s->queue);
     cudaFree(s->YH); cudaFree(s->tmp_nk); cudaFree(s->HTH); cudaFree(s->WTW); cudaFree(s->YtW); cudaFree(s->Cpart);
     cudaFree(s->lag_partial);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -551,7 +554,7 @@ extern "C" int trmf_b200_f_update(S *s) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
         if (f_update_tiled_supported(k) && (((uintptr_t)s->W) & 15) == 0 && !getenv("TRMF_B200_GENERIC_F")) {
             if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
-                                            s->lambdaI, (uint32_t)s->n, s->ticket + 1, &s->launches))
+                                            s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
                 return fail("f_update_tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else {
             const int ENT = 32;
@@ -615,7 +618,7 @@ extern "C" int trmf_b200_x_update(S *s) {
         if (gram_prepare(s)) return 1;
         if (s->gram_state == 1) {   // Grams of the (fixed) series factor over every time stamp's observed set
             if (f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
-                                             (uint32_t)s->T, s->ticket + 1, &s->launches))
+                                             (uint32_t)s->T, s->queue, &s->launches))
                 return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         if (fun_grad_launch(s, s->W, s->g)) return 1;
