@@ -64,6 +64,96 @@ __device__ __forceinline__ void grid_sum_commit(double block_val, double *part, 
     }
 }
 
+// Blocked variant of block_chol_solve (same contract, same layout): panels of 8 columns.
+// The panel (rows c0..n, 8 columns) is factored by warp 0 entirely in registers -- lane l owns
+// rows c0+l, c0+l+32, ... (SLOTS of them, so n+1 <= 32*SLOTS) and pivots travel by shuffle --
+// and the trailing matrix gets one rank-8 update by all threads: 2 CTA barriers per 8 columns
+// instead of 2 per column, no shared-memory round trip inside a panel, one rsqrt per pivot.
+template <int SLOTS>
+__device__ __forceinline__ void block_chol_solve_blocked(double *A, int ld, double *dinv, int n) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int tx = tid & 15, ty = tid >> 4, ny = blockDim.x >> 4;
+    for (int c0 = 0; c0 < n; c0 += 8) {
+        const int w = n - c0 < 8 ? n - c0 : 8;
+        __syncthreads();   // trailing update of the previous panel finished
+        if (tid < 32) {
+            double p[SLOTS][8];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int row = c0 + lane + 32 * s;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[s][q] = (row <= n && q < w) ? A[row * ld + c0 + q] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < w) {
+                    const double d = __shfl_sync(FULL_MASK, p[0][q], q);      // pivot A[c][c], c = c0 + q
+                    const double inv = rsqrt(d);
+                    if (lane == 0) dinv[c0 + q] = inv;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s)
+                        if (lane + 32 * s > q) p[s][q] *= inv;                 // rows below the pivot: L[i][c]
+#pragma unroll
+                    for (int q2 = q + 1; q2 < 8; ++q2) {
+                        const double lj = __shfl_sync(FULL_MASK, p[0][q], q2);  // L[c0+q2][c]
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s)
+                            if (lane + 32 * s >= q2) p[s][q2] -= p[s][q] * lj; // lower part of panel column q2
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int row = c0 + lane + 32 * s;
+                if (row <= n) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < w && lane + 32 * s > q) A[row * ld + c0 + q] = p[s][q];
+                }
+            }
+        }
+        __syncthreads();
+        // trailing update: A[i][j] -= sum_q L[i][c0+q] L[j][c0+q]   (i in (c0+w .. n], j in [c0+w .. min(i, n-1)])
+        const int t0 = c0 + w;
+        for (int i = t0 + ty; i <= n; i += ny) {
+            double li[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) li[q] = q < w ? A[i * ld + c0 + q] : 0.0;
+            const int jmax = i < n ? i : n - 1;
+            for (int j = t0 + tx; j <= jmax; j += 16) {
+                double acc = A[i * ld + j];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc -= li[q] * (q < w ? A[j * ld + c0 + q] : 0.0);
+                A[i * ld + j] = acc;
+            }
+        }
+    }
+    __syncthreads();
+    // backward substitution L^T x = y, warp 0; lane owns x[lane + 32 q]
+    if (tid < 32) {
+        double y[SLOTS];
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) { const int i = lane + 32 * q; y[q] = i < n ? A[n * ld + i] : 0.0; }
+        for (int c = n - 1; c >= 0; --c) {
+            const int q = c >> 5, owner = c & 31;
+            double v = y[0];
+#pragma unroll
+            for (int qq = 1; qq < SLOTS; ++qq) v = q == qq ? y[qq] : v;
+            v *= dinv[c];
+            v = __shfl_sync(FULL_MASK, v, owner);
+#pragma unroll
+            for (int qq = 0; qq < SLOTS; ++qq) {
+                const int i = lane + 32 * qq;
+                if (i == c) y[qq] = v;
+                else if (i < c) y[qq] -= A[c * ld + i] * v;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) { const int i = lane + 32 * q; if (i < n) A[n * ld + i] = y[q]; }
+    }
+    __syncthreads();
+}
+
 // Cholesky solve of an SPD system held in shared memory, by the whole CTA.
 //
 // Layout: `A` has n+1 rows of leading dimension ld (row-major, fp64).  Rows

@@ -42,6 +42,12 @@ namespace ft {
 // put exactly 3 Gram warps + 1 light warp on each of the SM's 4 schedulers (warp id % 4).
 constexpr int NT = 256;
 constexpr int NGRAM = 192;
+#ifndef TRMF_FT_MBAR
+#define TRMF_FT_MBAR 0   // 1: per-stage full/empty mbarriers (warps drift freely); 0: one __syncthreads per tile
+#endif                   // (measured equal at C2: 6.77 vs 6.79 ms; the barrier version issues 13 % fewer instructions)
+#ifndef TRMF_FT_FFMA2
+#define TRMF_FT_FFMA2 1  // 1: packed fma.rn.f32x2 (sm_100+: two IEEE fp32 FMAs per issue slot); 0: scalar FFMA
+#endif
 
 template <int K> struct Cfg {
     static constexpr int NB = (K + 7) / 8;
@@ -72,6 +78,15 @@ template <int K> struct Cfg {
     static constexpr int D = pick_d_();
 };
 
+// d.{x,y} += a.{x,y} * b.{x,y}: one FFMA2 (bitwise the same results as two fmaf)
+__device__ __forceinline__ void ffma2(float2 &d, const float2 a, const float2 b) {
+    unsigned long long dd = *reinterpret_cast<unsigned long long *>(&d);
+    const unsigned long long aa = *reinterpret_cast<const unsigned long long *>(&a);
+    const unsigned long long bb = *reinterpret_cast<const unsigned long long *>(&b);
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(dd) : "l"(aa), "l"(bb));
+    d = *reinterpret_cast<float2 *>(&dd);
+}
+
 // ---- cp.async (LDGSTS) primitives ----
 // (A TMA variant -- one cp.async.bulk per gathered 160-byte row, mbarrier completion -- was
 //  measured 3x slower end to end: per-row bulk requests are far too small for the copy engine.)
@@ -82,6 +97,28 @@ __device__ __forceinline__ void cp_async16(void *smem, const void *gmem, bool pr
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// ---- mbarrier primitives: per-stage "full" (data landed) / "empty" (all warps done) barriers ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// arrive once every cp.async this thread has issued so far has landed (counted in the barrier's expected arrivals)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t *bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
 
 template <int K>
 static size_t smem_bytes() {
@@ -120,6 +157,11 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
     float *rbuf = fbuf + C::FBUF;                                // KP/4 x 32 float4
     __shared__ unsigned next_series;
     __shared__ unsigned flavor_s;
+#if TRMF_FT_MBAR
+    // full[s]: the producer's copies into stage s have landed (32 cp.async-completion arrivals) and its tail
+    // zero fill is published (1 release arrival); empty[s]: the 7 consumer warps finished reading stage s
+    __shared__ __align__(8) uint64_t full_bar[STAGES], empty_bar[STAGES];
+#endif
 
     const int tid = threadIdx.x;
     const int lane = tid & 31, warp = tid >> 5;
@@ -131,9 +173,18 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         flavor_s = atomicAdd(sm_slots + smid, 1u) & 1u;
         next_series = atomicAdd(queue, 1u);
+#if TRMF_FT_MBAR
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 33); mbar_init(&empty_bar[s], NT / 32 - 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
     }
     __syncthreads();
     uint32_t j = next_series;
+#if TRMF_FT_MBAR
+    int r_stage = 0;          // ring position, running over the CTA's lifetime: consumers: next tile to read;
+    unsigned r_phase = 0;     // producer: next tile to issue (it runs STAGES-1 tiles ahead of the consumers)
+#endif
 
     // ---- roles ----
     // flavor 0: Gram warps 0,1,2,3,4,5   producer 6   rhs 7     (Gram per scheduler 2,2,1,1)
@@ -169,7 +220,7 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
             const int ntiles = (int)((nnz + ET - 1) / ET);
             for (int p = tid; p < (k + 1) * ld; p += NT) A[p] = 0.0;
 
-            float acc[8][8];
+            __align__(8) float acc[8][8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -179,8 +230,10 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
 
             // light-warp state (lane l <-> tile rows l, l+32, ...): producer: row indices of the next tile to
             // issue; rhs warp: Y values of the tile being consumed and of the next one
-            uint32_t nidx[NQ];
-            float vcur[NQ], vnext[NQ];
+            uint32_t lw[2 * NQ];          // producer: lw[0..NQ) = nidx;  rhs warp: lw[0..NQ) = vcur, lw[NQ..2NQ) = vnext (as bits)
+#define nidx lw
+#define VCUR(q) __uint_as_float(lw[q])
+#define VNEXT_SET(q, v) lw[NQ + (q)] = __float_as_uint(v)
             auto tile_count = [&](int tt) -> int {
                 const uint32_t rem = nnz - (uint32_t)tt * ET;
                 return (int)(rem < (uint32_t)ET ? rem : (uint32_t)ET);
@@ -198,10 +251,14 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
                     const uint32_t e = base + lane + 32 * q;
-                    vnext[q] = (lane + 32 * q < ET && e < nnz) ? __ldg(sval + e) : 0.f;
+                    VNEXT_SET(q, (lane + 32 * q < ET && e < nnz) ? __ldg(sval + e) : 0.f);
                 }
             };
             auto issue = [&](int tt, int stage) {   // producer warp: gathers tile tt (indices in nidx) into `stage`
+#if TRMF_FT_MBAR
+                stage = r_stage;
+                if (r_phase > 0) mbar_wait(&empty_bar[stage], (r_phase - 1) & 1u);   // previous tenant consumed by all
+#endif
                 float *dst = tiles + stage * STAGE_FLOATS + cp_dst;
                 const int cnt = tile_count(tt);
 #pragma unroll
@@ -217,8 +274,16 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                     }
                     cp_async16(dst + q * RPI * RS, cp_src + (size_t)row * k, cp_on && e < cnt);
                 }
+#if TRMF_FT_MBAR
+                mbar_arrive_on_cp_async(&full_bar[stage]);
+#endif
                 if (cnt < ET)   // tail tile: stale rows from an earlier tile must read as zero
                     for (int p = cnt * RS + lane; p < STAGE_FLOATS; p += 32) tiles[stage * STAGE_FLOATS + p] = 0.f;
+#if TRMF_FT_MBAR
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);   // release: publishes the zero fill
+                if (++r_stage == STAGES) { r_stage = 0; ++r_phase; }
+#endif
             };
             auto flush = [&]() {
 #pragma unroll
@@ -250,18 +315,33 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                         const int r = set_index<NB>(ti, h * 4 + (s4 >> 1));
                         const int c = set_index<NB>(tj, (s4 & 1) * 4 + c4);
                         if (r < k && c < k && !(ti == tj && r > c)) {
-                            double sum = 0.0;
-#pragma unroll 4
-                            for (int gg = 0; gg < G; ++gg) sum += (double)fbuf[(size_t)gg * 32 * B + u];
+                            // four independent fp64 chains (fixed association: still bitwise reproducible)
+                            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                            const float *fp = fbuf + u;
+#pragma unroll
+                            for (int gg = 0; gg + 3 < G; gg += 4) {
+                                s0 += (double)fp[(size_t)(gg + 0) * 32 * B];
+                                s1 += (double)fp[(size_t)(gg + 1) * 32 * B];
+                                s2 += (double)fp[(size_t)(gg + 2) * 32 * B];
+                                s3 += (double)fp[(size_t)(gg + 3) * 32 * B];
+                            }
+#pragma unroll
+                            for (int gg = G & ~3; gg < G; ++gg) s0 += (double)fp[(size_t)gg * 32 * B];
                             const int hi_ = r > c ? r : c, lo_ = r > c ? c : r;
-                            A[hi_ * ld + lo_] += sum;
+                            A[hi_ * ld + lo_] += (s0 + s1) + (s2 + s3);
                         }
                     }
                     if (h == 0 && tid < k) {
-                        double sum = 0.0;
-#pragma unroll 8
-                        for (int l = 0; l < 32; ++l) sum += (double)rbuf[((tid >> 2) * 32 + l) * 4 + (tid & 3)];
-                        A[k * ld + tid] += sum;
+                        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                        const float *rp = rbuf + (tid >> 2) * 128 + (tid & 3);
+#pragma unroll
+                        for (int l = 0; l < 32; l += 4) {
+                            s0 += (double)rp[(l + 0) * 4];
+                            s1 += (double)rp[(l + 1) * 4];
+                            s2 += (double)rp[(l + 2) * 4];
+                            s3 += (double)rp[(l + 3) * 4];
+                        }
+                        A[k * ld + tid] += (s0 + s1) + (s2 + s3);
                     }
                     __syncthreads();
                 }
@@ -284,26 +364,20 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
 
             int stage = 0;                         // stage holding tile t
             for (int t = 0; t < ntiles; ++t) {
+#if TRMF_FT_MBAR
+                if (is_prod) {
+                    // the producer runs ahead on its own: refill the ring as soon as every consumer warp has
+                    // released the stage (empty barrier), no CTA-wide barrier involved
+                    const int nt = t + STAGES - 1;
+                    if (nt < ntiles) issue(nt, 0);
+                    if (nt + 1 < ntiles) load_idx(nt + 1);
+                } else {
+                    stage = r_stage;
+                    mbar_wait(&full_bar[stage], r_phase & 1u);   // tile t has landed
+#else
                 if (is_prod) cp_async_wait<STAGES - 2>();   // the producer issued every copy of tile t
                 __syncthreads();                   // tile t is visible to everyone; tile t-1 is fully consumed
-                if (is_gram) {
-                    if (active) {
-                        const float *pa = tiles + stage * STAGE_FLOATS + off_a, *pb = tiles + stage * STAGE_FLOATS + off_b;
-#pragma unroll
-                        for (int u = 0; u < U; ++u) {
-                            const float4 a0 = *reinterpret_cast<const float4 *>(pa + u * G * RS);
-                            const float4 a1 = *reinterpret_cast<const float4 *>(pa + u * G * RS + 4 * NB);
-                            const float4 b0 = *reinterpret_cast<const float4 *>(pb + u * G * RS);
-                            const float4 b1 = *reinterpret_cast<const float4 *>(pb + u * G * RS + 4 * NB);
-                            const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-#pragma unroll
-                            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                                for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(a[i], bv[jj], acc[i][jj]);
-                        }
-                    }
-                } else if (is_prod) {
+                if (is_prod) {
                     const int nt = t + STAGES - 1;
                     int ns = stage + STAGES - 1;
                     if (ns >= STAGES) ns -= STAGES;
@@ -311,35 +385,78 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                     cp_async_commit();
                     if (nt + 1 < ntiles) load_idx(nt + 1);
                 } else {
+#endif
+                    if (is_gram) {
+                        if (active) {
+                            const float *pa = tiles + stage * STAGE_FLOATS + off_a, *pb = tiles + stage * STAGE_FLOATS + off_b;
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) vcur[q] = vnext[q];
-                    if (t + 1 < ntiles) load_vals(t + 1);
-                    const float *tb = tiles + stage * STAGE_FLOATS;
+                            for (int u = 0; u < U; ++u) {
+                                const float4 a0 = *reinterpret_cast<const float4 *>(pa + u * G * RS);
+                                const float4 a1 = *reinterpret_cast<const float4 *>(pa + u * G * RS + 4 * NB);
+                                const float4 b0 = *reinterpret_cast<const float4 *>(pb + u * G * RS);
+                                const float4 b1 = *reinterpret_cast<const float4 *>(pb + u * G * RS + 4 * NB);
+                                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+#if TRMF_FT_FFMA2
+                                const float2 bp[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w),
+                                                      make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int e = lane + 32 * q;     // rows past the tile's count are zero and carry y = 0
-                        if (e < ET) {
-                            const float y = vcur[q];
-                            const float *row = tb + e * RS;
+                                for (int i = 0; i < 8; ++i) {
+                                    const float2 ap = make_float2(a[i], a[i]);
 #pragma unroll
-                            for (int c4 = 0; c4 < KP / 4; ++c4) {
-                                const float4 w = *reinterpret_cast<const float4 *>(row + 4 * c4);
-                                RACC(4 * c4 + 0) = fmaf(y, w.x, RACC(4 * c4 + 0));
-                                RACC(4 * c4 + 1) = fmaf(y, w.y, RACC(4 * c4 + 1));
-                                RACC(4 * c4 + 2) = fmaf(y, w.z, RACC(4 * c4 + 2));
-                                RACC(4 * c4 + 3) = fmaf(y, w.w, RACC(4 * c4 + 3));
+                                    for (int jp = 0; jp < 4; ++jp)
+                                        ffma2(*reinterpret_cast<float2 *>(&acc[i][2 * jp]), ap, bp[jp]);
+                                }
+#else
+                                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                                    for (int jj = 0; jj < 8; ++jj) acc[i][jj] = fmaf(a[i], bv[jj], acc[i][jj]);
+#endif
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) lw[q] = lw[NQ + q];
+                        if (t + 1 < ntiles) load_vals(t + 1);
+                        const float *tb = tiles + stage * STAGE_FLOATS;
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const int e = lane + 32 * q;     // rows past the tile's count are zero and carry y = 0
+                            if (e < ET) {
+                                const float y = VCUR(q);
+                                const float *row = tb + e * RS;
+#pragma unroll
+                                for (int c4 = 0; c4 < KP / 4; ++c4) {
+                                    const float4 w = *reinterpret_cast<const float4 *>(row + 4 * c4);
+                                    RACC(4 * c4 + 0) = fmaf(y, w.x, RACC(4 * c4 + 0));
+                                    RACC(4 * c4 + 1) = fmaf(y, w.y, RACC(4 * c4 + 1));
+                                    RACC(4 * c4 + 2) = fmaf(y, w.z, RACC(4 * c4 + 2));
+                                    RACC(4 * c4 + 3) = fmaf(y, w.w, RACC(4 * c4 + 3));
+                                }
                             }
                         }
                     }
+#if TRMF_FT_MBAR
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[stage]);   // this warp is done with tile t's stage
+                    if (++r_stage == STAGES) { r_stage = 0; ++r_phase; }
+#endif
                 }
+#if !TRMF_FT_MBAR
                 if (++stage == STAGES) stage = 0;
+#endif
                 if ((t + 1) % C::FL == 0 && t + 1 < ntiles) flush();
             }
+#if TRMF_FT_MBAR
+            // bring the producer's ring position in line with the consumers' for the next series: it has issued
+            // exactly ntiles tiles, like they have consumed (prologue + loop), so both counters already agree
+#endif
             if (is_prod) cp_async_wait<0>();
             flush();   // ends with __syncthreads
             if (SOLVE) {
                 if (tid < k) A[tid * ld + tid] += lambda;      // trmf.cpp:393
-                block_chol_solve(A, ld, dinv, k);              // starts and ends with __syncthreads
+                block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, k);   // starts and ends with __syncthreads
                 if (tid < k) F[(size_t)j * k + tid] = (float)A[k * ld + tid];
             } else {
                 float *Gj = Gout + (size_t)j * k * k;
@@ -350,6 +467,9 @@ f_update_tiled_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restri
                 if (tid < k) F[(size_t)j * k + tid] = (float)A[k * ld + tid];
             }
 #undef RACC
+#undef nidx
+#undef VCUR
+#undef VNEXT_SET
         } else if (!SOLVE) {
             float *Gj = Gout + (size_t)j * k * k;
             for (int p = tid; p < k * k; p += NT) Gj[p] = 0.f;

@@ -12,7 +12,7 @@
 #pragma once
 #include "common.cuh"
 
-#define TRMF_MAX_LAGS 512
+#define TRMF_MAX_LAGS 128   // block_chol_solve keeps the solution in 4 registers per lane: systems up to 128 x 128
 
 struct LagSet {           // passed by value (kernel parameter space)
     int L;
