@@ -11,6 +11,7 @@
 #include "f_update.cuh"
 #include "f_update_tiled.cuh"
 #include "x_update.cuh"
+#include "x_pass_fast.cuh"
 #include "lag_update.cuh"
 #include "dense.cuh"
 
@@ -389,6 +390,15 @@ template <int MODE>
 static int sparse_pass(S *s, const uint64_t *ptr, const uint32_t *col, const V *val, const V *Hm, const V *Sv, V *out,
                        size_t rows, int fslot, bool accum = true) {
     const int k = s->k;
+    if (MODE != MODE_SPMM && x_pass_fast_supported(k) && ((((uintptr_t)Hm) | ((uintptr_t)Sv) | ((uintptr_t)out)) & 15) == 0 &&
+        rows < 0xffffffffull && !getenv("TRMF_B200_GENERIC_PASS")) {
+        double *fo = s->scal + (fslot >= 0 ? fslot : SC_TMP);
+        if (x_pass_fast_launch<MODE>(s->stream, s->num_sms, ptr, col, val, Hm, Sv, out, k, (uint32_t)rows, accum, s->queue,
+                                     s->part, s->ticket, fo))
+            return fail("x_pass_fast launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        s->launches++;
+        return 0;
+    }
     const int WARPS = 4;
     const size_t smem = sparse_pass_smem(k, WARPS);
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((rows + WARPS - 1) / WARPS, (size_t)s->num_sms * 8));
