@@ -20,6 +20,8 @@
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
+#include <ctime>
 #include <random>
 #include <string>
 #include <vector>
@@ -58,6 +60,11 @@ struct trmf_b200_session {
     int num_sms = 148;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // host-buffer sessions: the by-time CSR (first needed by the X-update) is uploaded on a second stream so
+    // that the copy overlaps the F-update, which only reads the by-series CSC
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t csr_ready = nullptr;
+    bool csr_pending = false;
 
     size_t T = 0, n = 0, nnz = 0;
     int k = 0, L = 0, mid = 0;
@@ -106,6 +113,8 @@ struct trmf_b200_session {
     // X-update through per-time-stamp Grams (fp32 build, k % 4 == 0, k <= 64)
     V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
     int gram_state = 0;               // 0 = not decided, 1 = enabled, -1 = disabled
+    int prev_cg = -1;                 // CG steps of the previous x_update of this session (-1: none yet)
+    bool gram_now = false;            // this x_update goes through the Grams
     unsigned long long collectives = 0;
 
     double lambdaI = 0.1, lambdaAR = 0.1, lambdaLag = 0.1;
@@ -142,12 +151,45 @@ static inline unsigned ew_grid(const S *s, size_t n, int threads = 256) {
     return (unsigned)std::max<size_t>(1, std::min(b, cap));
 }
 
+// Device memory comes from the device's default stream-ordered pool with the release threshold
+// lifted, so the buffers of one c_trmf_train call are recycled by the next one instead of going
+// through cudaMalloc/cudaFree (measured: 50-640 ms per call for the 1.5 GB of a C2 session).
+static int pool_setup(int device) {
+    static bool done[64] = {false};
+    if (device < 0 || device >= 64 || done[device]) return 0;
+    cudaMemPool_t pool;
+    CUDA_TRY(cudaDeviceGetDefaultMemPool(&pool, device));
+    unsigned long long keep = ~0ull;
+    CUDA_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    done[device] = true;
+    return 0;
+}
+
 template <typename T>
-static int dev_alloc(T **p, size_t count) {
+static int dev_alloc_on(cudaStream_t st, T **p, size_t count) {
     *p = nullptr;
     if (count == 0) count = 1;
-    CUDA_TRY(cudaMalloc((void **)p, count * sizeof(T)));
+    CUDA_TRY(cudaMallocAsync((void **)p, count * sizeof(T), st));
     return 0;
+}
+#define dev_alloc(ptr, count) dev_alloc_on(s->stream, ptr, count)
+#define dev_free(ptr) do { if (ptr) cudaFreeAsync((void *)(ptr), s->stream); } while (0)
+
+// pinned host scratch (the scalar mirror) is recycled across sessions as well
+static std::vector<double *> g_pinned_free;
+static std::mutex g_pinned_mu;
+static int pinned_get(double **p) {
+    {
+        std::lock_guard<std::mutex> lk(g_pinned_mu);
+        if (!g_pinned_free.empty()) { *p = g_pinned_free.back(); g_pinned_free.pop_back(); return 0; }
+    }
+    CUDA_TRY(cudaMallocHost((void **)p, SC_COUNT * sizeof(double)));
+    return 0;
+}
+static void pinned_put(double *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_pinned_mu);
+    g_pinned_free.push_back(p);
 }
 
 // --------------------------------------------------------------------------
@@ -161,6 +203,7 @@ static int session_common_init(S *s) {
     if (prop.major < 10)
         return fail("device %d (%s, sm_%d%d) is not a Blackwell (sm_100a) GPU; this library has no other code path",
                     s->device, prop.name, prop.major, prop.minor);
+    if (pool_setup(s->device)) return 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
     const size_t tk = s->T * (size_t)s->k;
@@ -172,7 +215,7 @@ static int session_common_init(S *s) {
         return 1;
     CUDA_TRY(cudaMemsetAsync(s->scal, 0, SC_COUNT * sizeof(double), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->ticket, 0, 4 * sizeof(unsigned), s->stream));
-    CUDA_TRY(cudaMallocHost((void **)&s->h_scal, SC_COUNT * sizeof(double)));
+    if (pinned_get(&s->h_scal)) return 1;
     if (dev_alloc(&s->lags_dev, s->lags.size())) return 1;
     CUDA_TRY(cudaMemcpyAsync(s->lags_dev, s->lags.data(), s->lags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
     // lag update: chunk the window so that (chunk + mid) fp64 values fit in shared memory
@@ -224,27 +267,31 @@ static int check_lags(S *s, const uint32_t *lag_set, uint32_t lag_size) {
 extern "C" void trmf_b200_destroy(S *s) {
     if (!s) return;
     cudaSetDevice(s->device);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
-    cudaFree(s->part_tk);
-    cudaFree(s->Gt); cudaFree(s->bt);
+    dev_free(s->part_tk);
+    dev_free(s->Gt); dev_free(s->bt);
     if (s->own_Y) {
-        cudaFree(s->row_ptr); cudaFree(s->col_ptr); cudaFree(s->col_idx); cudaFree(s->row_idx);
-        cudaFree(s->val_t); cudaFree(s->val); cudaFree(s->Yd);
+        dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
+        dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
     }
-    if (s->own_factors) { cudaFree(s->W); cudaFree(s->H); cudaFree(s->th); }
-    cudaFree(s->lags_dev);
-    cudaFree(s->W_sv); cudaFree(s->H_sv); cudaFree(s->th_sv);
-    cudaFree(s->g); cudaFree(s->s); cudaFree(s->r); cudaFree(s->d); cudaFree(s->Hd); cudaFree(s->wnew);
-    cudaFree(s->rho); cudaFree(s->scal); cudaFree(s->part); cudaFree(s->ticket); cudaFree(s->queue);
-    cudaFree(s->YH); cudaFree(s->tmp_nk); cudaFree(s->HTH); cudaFree(s->WTW); cudaFree(s->YtW); cudaFree(s->Cpart);
-    cudaFree(s->lag_partial);
-    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->own_factors) { dev_free(s->W); dev_free(s->H); dev_free(s->th); }
+    dev_free(s->lags_dev);
+    dev_free(s->W_sv); dev_free(s->H_sv); dev_free(s->th_sv);
+    dev_free(s->g); dev_free(s->s); dev_free(s->r); dev_free(s->d); dev_free(s->Hd); dev_free(s->wnew);
+    dev_free(s->rho); dev_free(s->scal); dev_free(s->part); dev_free(s->ticket); dev_free(s->queue);
+    dev_free(s->YH); dev_free(s->tmp_nk); dev_free(s->HTH); dev_free(s->WTW); dev_free(s->YtW); dev_free(s->Cpart);
+    dev_free(s->lag_partial);
+    pinned_put(s->h_scal);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->ev3) cudaEventDestroy(s->ev3);
+    if (s->stream) cudaStreamSynchronize(s->stream);   // the frees above are ordered on the stream
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->csr_ready) cudaEventDestroy(s->csr_ready);
     delete s;
 }
 
@@ -279,10 +326,22 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     if (session_common_init(s)) return 1;
     s->own_Y = true;
     if (s->sparse_storage) {
-        if (h2d_new(s, &s->row_ptr, Y->row_ptr, s->T + 1) || h2d_new(s, &s->col_idx, Y->col_idx, s->nnz) ||
-            h2d_new(s, &s->val_t, Y->val_t, s->nnz) || h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) ||
-            h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) || h2d_new(s, &s->val, Y->val, s->nnz))
+        if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) || h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) ||
+            h2d_new(s, &s->val, Y->val, s->nnz))
             return 1;
+        // by-time CSR: allocate in stream order, copy on the side stream, publish with an event
+        if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->col_idx, s->nnz) || dev_alloc(&s->val_t, s->nnz)) return 1;
+        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->csr_ready, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));                 // the allocations are ordered on s->stream
+        CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
+        CUDA_TRY(cudaMemcpyAsync(s->row_ptr, Y->row_ptr, (s->T + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
+        if (s->nnz) {
+            CUDA_TRY(cudaMemcpyAsync(s->col_idx, Y->col_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+            CUDA_TRY(cudaMemcpyAsync(s->val_t, Y->val_t, s->nnz * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
+        }
+        CUDA_TRY(cudaEventRecord(s->csr_ready, s->copy_stream));
+        s->csr_pending = true;
     } else {
         if (h2d_new(s, &s->Yd, Y->val, s->T * s->n)) return 1;
     }
@@ -340,6 +399,8 @@ extern "C" int trmf_b200_set_params(S *s, double lambdaI, double lambdaAR, doubl
 
 extern "C" int trmf_b200_set_stream(S *s, void *cuda_stream) {
     CUDA_TRY(cudaSetDevice(s->device));
+    if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    s->csr_pending = false;
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     s->stream = (cudaStream_t)cuda_stream;
@@ -350,6 +411,14 @@ extern "C" int trmf_b200_enable_timing(S *s, int32_t on) { s->timing = on != 0; 
 extern "C" int trmf_b200_sync(S *s) {
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaStreamSynchronize(s->stream));
+    return 0;
+}
+
+// make the session stream wait for the side-stream upload of the by-time CSR (first consumer calls this)
+static int need_csr(S *s) {
+    if (!s->csr_pending) return 0;
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
+    s->csr_pending = false;
     return 0;
 }
 
@@ -617,6 +686,7 @@ extern "C" int trmf_b200_x_update(S *s) {
     g_last_error.clear();
     CUDA_TRY(cudaSetDevice(s->device));
     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
+    if (need_csr(s)) return 1;
     const size_t tk = s->T * (size_t)s->k;
     const unsigned eg = ew_grid(s, tk);
     const double eps_cg = 0.1, eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
@@ -626,7 +696,11 @@ extern "C" int trmf_b200_x_update(S *s) {
     int cur = SC_RTR, nxt = SC_RNEW;
     if (s->missing) {
         if (gram_prepare(s)) return 1;
-        if (s->gram_state == 1) {   // Grams of the (fixed) series factor over every time stamp's observed set
+        // Building the Grams costs about three walks over Omega (measured at C2: 6.3 ms vs 2.1 ms per Hv walk), so
+        // it pays off from ~4 CG steps on; the previous X-update's step count is the predictor (ALS needs fewer and
+        // fewer CG steps as it converges).  TRMF_B200_FORCE_GRAM_HV pins the choice for tests.
+        s->gram_now = s->gram_state == 1 && (s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
+        if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
             if (f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
                                              (uint32_t)s->T, s->queue, &s->launches))
                 return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -653,7 +727,7 @@ extern "C" int trmf_b200_x_update(S *s) {
             if (rnorm <= cgtol) break;
             if (cg_iter >= max_cg) break;
             ++cg_iter;
-            if (s->missing && s->gram_state == 1) {
+            if (s->missing && s->gram_now) {
                 if (gram_hv_launch(s, s->d, s->Hd, true)) return 1;
             } else {
                 if (hv_launch(s, s->d, s->Hd)) return 1;
@@ -685,6 +759,7 @@ extern "C" int trmf_b200_x_update(S *s) {
         else if (actred < eta1 * prered) delta = std::max(sigma1 * delta, std::min(alpha * snorm, sigma2 * delta));
         else if (actred < eta2 * prered) delta = std::max(sigma1 * delta, std::min(alpha * snorm, sigma3 * delta));
         else delta = std::max(delta, std::min(alpha * snorm, sigma3 * delta));
+        s->prev_cg = (int)cg_iter;
         s->st_cg = (double)cg_iter; s->st_fnew = fnew; s->st_prered = prered; s->st_actred = actred;
         s->st_delta = delta; s->st_rnorm = rnorm;
         if (actred > eta0 * prered) {
@@ -892,14 +967,29 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     }
     if (!check_dimension(pyY, py_lag_size, pyW, pyH, pylag_val)) return;
     (void)threads;   // OpenMP thread count of the reference (trmf.cpp:636): no meaning here
+    const bool trace = getenv("TRMF_B200_TRACE") != nullptr;   // host-side wall-clock split of the call, to stderr
+    auto now_ms = []() {
+        struct timespec tw;
+        clock_gettime(CLOCK_MONOTONIC, &tw);
+        return tw.tv_sec * 1e3 + tw.tv_nsec * 1e-6;
+    };
+    const double t0 = now_ms();
     S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, 0);
     if (!s) return;   // message already on stderr
+    double t1 = now_ms();
+    if (trace) { cudaStreamSynchronize(s->stream); t1 = now_ms(); }
     trmf_b200_set_params(s, lambdaI, lambdaAR, lambdaLag);
-    if (trmf_b200_train(s, max_iter, period_W, period_H, period_Lag, verbose) == 0)
-        trmf_b200_download(s, pyW->val, pyH->val, pylag_val->val);
+    const int rc = trmf_b200_train(s, max_iter, period_W, period_H, period_Lag, verbose);
+    double t2 = now_ms();
+    if (trace) { cudaStreamSynchronize(s->stream); t2 = now_ms(); }
+    if (rc == 0) trmf_b200_download(s, pyW->val, pyH->val, pylag_val->val);
+    const double t3 = now_ms();
     std::string keep = g_last_error;
     trmf_b200_destroy(s);
     g_last_error = keep;
+    if (trace)
+        fprintf(stderr, "[trmf-b200 trace] create+H2D %.2f ms, train %.2f ms, D2H %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1,
+                t3 - t2, now_ms() - t3);
 }
 
 #include "extras.cuh"   // multi-GPU (NCCL) and on-device synthetic data

@@ -209,3 +209,35 @@ def test_python_surface_end_to_end():
         trmf.trmf._clib.train = real_train
     for a, b in zip(met, met_o):
         assert np.isfinite(a) and abs(a - b) <= 1e-6 * max(1.0, abs(b))
+
+
+@pytest.mark.parametrize("env", [{"TRMF_B200_GENERIC_F": "1"}, {"TRMF_B200_NO_GRAM_HV": "1"}, {"TRMF_B200_GENERIC_PASS": "1"},
+                                 {"TRMF_B200_FORCE_GRAM_HV": "1"},
+                                 {"TRMF_B200_GENERIC_F": "1", "TRMF_B200_NO_GRAM_HV": "1", "TRMF_B200_GENERIC_PASS": "1"}])
+def test_float32_kernel_variants_agree(env, monkeypatch):
+    """Every fp32 kernel variant (tiled / generic F kernel, Gram-based / direct Hv, fast / generic walk over
+    Omega) stays within the 1e-5 bar of the float64 oracle, over two outer iterations each started from the
+    oracle's factors (so the adaptive Gram/direct choice of the second X-update is exercised too)."""
+    for name, value in env.items():
+        monkeypatch.setenv(name, value)
+    from trmf.session import Session
+    p = cases.make_problem(900, 700, 40, [1, 7, 24], 0.7, seed=55)
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    Y = sps.csr_matrix((f32(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    lam = (0.5, 50.0, 0.5)
+    W, H, L = (f32(p[x]).astype(np.float64) for x in ("W0", "H0", "L0"))
+    s = Session(Y, p["lags"], f32(W), f32(H), f32(L), missing=True, dtype=np.float32, lambdaI=lam[0], lambdaAR=lam[1], lambdaLag=lam[2])
+    Y64 = Y.astype(np.float64)
+    for it in range(2):
+        s.upload(W=f32(W), H=f32(H), lag_val=f32(L))
+        W, H, L = f32(W).astype(np.float64), f32(H).astype(np.float64), f32(L).astype(np.float64)
+        s.f_update(); s.x_update(); s.lag_update()
+        Ho = tn.f_update_sparse(sps.csc_matrix(Y64), W, H, lam[0])
+        info = {}
+        Wo = tn.x_update(tn.SparseLoss(Y64, Ho), W, p["lags"].astype(np.int64), L, lam[0], lam[1], info)
+        Lo = tn.lag_update(Wo, p["lags"], lam[2])
+        Wg, Hg, Lg = s.download()
+        assert int(s.stat("cg_iters")) == info["cg_iter"]
+        assert cases.rel(Hg, Ho) < TOL32 and cases.rel(Wg, Wo) < TOL32 and cases.rel(Lg, Lo) < TOL32
+        W, H, L = Wo, Ho, Lo
+    s.close()
