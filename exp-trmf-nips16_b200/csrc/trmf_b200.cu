@@ -324,6 +324,12 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         return fail("unsupported PyMatrix type %d for Y", Y->type);
     }
     if (session_common_init(s)) return 1;
+    // factors first: the H2D engine serves copies in submission order, and the F-update must not queue
+    // behind the side-stream upload of the by-time CSR
+    s->own_factors = true;
+    if (h2d_new(s, &s->W, W->val, s->T * (size_t)s->k) || h2d_new(s, &s->H, H->val, s->n * (size_t)s->k) ||
+        h2d_new(s, &s->th, lag_val->val, (size_t)s->L * s->k))
+        return 1;
     s->own_Y = true;
     if (s->sparse_storage) {
         if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) || h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) ||
@@ -345,10 +351,6 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     } else {
         if (h2d_new(s, &s->Yd, Y->val, s->T * s->n)) return 1;
     }
-    s->own_factors = true;
-    if (h2d_new(s, &s->W, W->val, s->T * (size_t)s->k) || h2d_new(s, &s->H, H->val, s->n * (size_t)s->k) ||
-        h2d_new(s, &s->th, lag_val->val, (size_t)s->L * s->k))
-        return 1;
     return 0;
 }
 
