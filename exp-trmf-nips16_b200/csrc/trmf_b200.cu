@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "f_update.cuh"
 #include "f_update_tiled.cuh"
+#include "f_update_mma.cuh"
 #include "x_update.cuh"
 #include "x_pass_fast.cuh"
 #include "lag_update.cuh"
@@ -430,6 +431,22 @@ static int read_scalars(S *s) {
     return 0;
 }
 
+// Which Gram kernel serves a sparse F-update / Gram build of rank k over the factor at `X`:
+//   mma   3xTF32 mma.sync tiles (f_update_mma.cuh)   -- default where supported
+//   ffma  register-tiled FFMA kernel (f_update_tiled.cuh)
+//   generic  any k <= 128, any alignment, fp64 build (f_update.cuh)
+// TRMF_B200_F_KERNEL=mma|ffma|generic pins the choice (tests, before/after profiles).
+enum { F_KERNEL_GENERIC = 0, F_KERNEL_FFMA = 1, F_KERNEL_MMA = 2 };
+static int f_kernel_choice(int k, const V *X) {
+    const char *e = getenv("TRMF_B200_F_KERNEL");
+    if (getenv("TRMF_B200_GENERIC_F") || (e && !strcmp(e, "generic"))) return F_KERNEL_GENERIC;
+    if ((((uintptr_t)X) & 15) != 0) return F_KERNEL_GENERIC;
+    const bool want_ffma = e && !strcmp(e, "ffma");
+    if (!want_ffma && f_update_mma_supported(k)) return F_KERNEL_MMA;
+    if (f_update_tiled_supported(k)) return F_KERNEL_FFMA;
+    return F_KERNEL_GENERIC;
+}
+
 // --------------------------------------------------------------------------
 // building blocks
 // --------------------------------------------------------------------------
@@ -592,8 +609,7 @@ static int fun_grad_launch(S *s, const V *w, V *g) {
 static int gram_prepare(S *s) {
     if (s->gram_state != 0) return 0;
     s->gram_state = -1;
-    if (!s->missing || !f_update_tiled_supported(s->k) || getenv("TRMF_B200_NO_GRAM_HV")) return 0;
-    if ((((uintptr_t)s->H) & 15) != 0) return 0;
+    if (!s->missing || f_kernel_choice(s->k, s->H) == F_KERNEL_GENERIC || getenv("TRMF_B200_NO_GRAM_HV")) return 0;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     const size_t need = (s->T * (size_t)s->k * s->k + s->T * (size_t)s->k) * sizeof(V);
@@ -633,7 +649,12 @@ extern "C" int trmf_b200_f_update(S *s) {
     const int k = s->k;
     if (s->missing) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
-        if (f_update_tiled_supported(k) && (((uintptr_t)s->W) & 15) == 0 && !getenv("TRMF_B200_GENERIC_F")) {
+        const int fk = f_kernel_choice(k, s->W);
+        if (fk == F_KERNEL_MMA) {
+            if (f_update_mma_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
+                                          s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
+                return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (fk == F_KERNEL_FFMA) {
             if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
                                             s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
                 return fail("f_update_tiled launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -703,9 +724,14 @@ extern "C" int trmf_b200_x_update(S *s) {
         // fewer CG steps as it converges).  TRMF_B200_FORCE_GRAM_HV pins the choice for tests.
         s->gram_now = s->gram_state == 1 && (s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
         if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
-            if (f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
-                                             (uint32_t)s->T, s->queue, &s->launches))
-                return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            int rc;
+            if (f_kernel_choice(s->k, s->H) == F_KERNEL_MMA)
+                rc = f_update_mma_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
+                                                (uint32_t)s->T, s->queue, &s->launches);
+            else
+                rc = f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
+                                                  (uint32_t)s->T, s->queue, &s->launches);
+            if (rc) return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
         if (fun_grad_launch(s, s->W, s->g)) return 1;
     } else {
