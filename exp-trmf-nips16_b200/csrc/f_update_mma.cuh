@@ -1,30 +1,38 @@
-// f_update_mma.cuh -- K1 on the warp-level tensor path: per-series Gram by 3xTF32 mma.sync + fp64 Cholesky
+// f_update_mma.cuh -- K1 on the warp-level tensor path: per-series Gram by split-fp16 mma.sync + fp64 Cholesky
 // (fp32 storage build only).
 //
 // Replaces the hot loop of l2r_ls_pY_IX_chol::solve (reference trmf.cpp:382-395): per observed entry the
 // reference does k(k+1)/2 + k scalar multiply-adds into a k x k buffer.  The Gram G = sum_e x_e x_e^T is a
 // SYRK with M = N = k <= 64 and K = |Omega_j|.  tcgen05 cannot be fed by it (its tile is 128 rows of ONE
-// accumulator; a series' Gram has k <= 64 and different series have different K ranges), but the warp-level
-// m16n8k8 TF32 tile fits any k: a warp holds the whole upper triangle of the Gram as NT 16x8 accumulator tiles
-// (9 at k = 40) and per 8 observed entries issues NT x 3 HMMAs.  Measured on B200
-// (tools/microbench_mma.cu): 512 TF32 MAC/clk/SM from mma.sync, 9.5 clk per entry per SM for this loop at
-// k = 40, against 20 clk per entry per SM for the FFMA formulation (f_update_tiled.cuh).
+// accumulator; a series' Gram has k <= 64 rows and every series its own K range), but the warp-level
+// m16n8k16 tile fits any k: a warp holds the whole upper triangle of the Gram as NT 16x8 accumulator tiles
+// (9 at k = 40) and per 16 observed entries issues NT x 3 HMMAs.
+//
+// Measured on B200 (tools/microbench_mma.cu, microbench_mma2.cu; profiles/): a legacy HMMA (TF32 m16n8k8 or
+// fp16 m16n8k16 alike) holds the SM sub-partition's issue port for 8 clk and every other instruction adds 1 clk
+// on top (strictly additive), so the cost of this loop is 8 x #HMMA + #other instructions.  That is why the
+// operands are fp16 pairs (2048 MACs per HMMA) rather than TF32 (1024): 6.0 against 9.5 clk per entry per SM
+// for the bare loop at k = 40, and 20 clk per entry per SM for the FFMA formulation (f_update_tiled.cuh).
 //
 // Accuracy (the 1e-5 parity bar is on the factors; the fp32 reference build itself is 1e-5 off its fp64 twin):
-//  * 3xTF32 split: x = hi + lo with hi = x rounded to TF32 (11 significant bits), lo = x - hi (exact, |lo| <=
-//    2^-12 |x|, read by the tensor core through its own truncation to TF32); the product keeps hi*hi + hi*lo
-//    + lo*hi and drops lo*lo (2^-24 relative);
-//  * the tensor core adds with truncation, so it is only trusted with the 8 entries x 3 terms of one chunk
-//    (small terms first); chunks are summed by FADD (round to nearest) for at most 128 entries and those
-//    partial sums go into per-warp fp64 accumulators in shared memory.  Measured Gram error against fp64:
-//    7.8e-8 relative Frobenius, -4.5e-8 mean (direct tensor-core accumulation over 128 entries: -1.1e-6 bias).
+//  * the factor is first scaled per latent dimension by a power of two so that its largest magnitude lands in
+//    [2^14, 2^15) (colscale kernels below; exact, undone exactly in the epilogue) -- fp16's narrow exponent
+//    range then covers 2^-17 of every column's maximum with full precision and everything below with an
+//    absolute error of 2^-39 of that maximum;
+//  * split: x = h1 + h2, h1 = fp16(x), h2 = fp16(x - h1): 22 significant bits; the product keeps h1*h1 + h1*h2
+//    + h2*h1 and drops h2*h2 (2^-22 relative to the dropped-term-free product's own rounding);
+//  * the tensor core adds with truncation, so it is only trusted with the 16 entries x 3 terms of one tile
+//    (small terms first); tiles are summed by FADD (round to nearest) for at most 128 entries and those partial
+//    sums go into per-warp fp64 accumulators in shared memory.  Measured Gram error against fp64 over 128
+//    entries: 7.0e-8 relative Frobenius, -4.5e-8 mean (tensor-core accumulation over 128 entries instead:
+//    -1.1e-6 bias).
 //
 // Work decomposition: CTA = NW warps, one series at a time (atomic queue).  The series' entries are cut into
 // tiles of 16; warp w takes tiles w, w + NW, ...  Each warp runs its own 3-stage cp.async (LDGSTS) pipeline
 // (16 factor rows of k floats per stage, the Y values ride along with 4-byte copies) -- no CTA barrier inside
 // a series.  Fragment loads are bank-conflict free because the staging row stride RS = 8 (mod 16) floats.
-// At the end of a series the NW fp64 partials are added in warp order (bitwise reproducible), lambda goes on
-// the diagonal and the CTA runs the blocked fp64 Cholesky of common.cuh.
+// At the end of a series the NW fp64 partials are added in warp order (bitwise reproducible), the scaling is
+// undone, lambda goes on the diagonal and the CTA runs the blocked fp64 Cholesky of common.cuh.
 #pragma once
 #include "common.cuh"
 
@@ -32,7 +40,7 @@
 
 namespace fm {
 
-constexpr int ET = 16;        // entries per tile (two m16n8k8 K-steps)
+constexpr int ET = 16;        // entries per tile (one m16n8k16 K-step)
 constexpr int FLUSH = 8;      // tiles between fp32 -> fp64 flushes (128 entries)
 
 template <int K> struct Cfg {
@@ -66,34 +74,79 @@ __device__ __forceinline__ void cp_async4(float *smem, const float *gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// x = hi + lo: hi = x rounded (half away) to 11 significant bits, lo = the exact remainder
-__device__ __forceinline__ void split_tf32(const float v, uint32_t &hi, uint32_t &lo) {
-    hi = (__float_as_uint(v) + 0x1000u) & 0xffffe000u;
-    lo = __float_as_uint(v - __uint_as_float(hi));
+// two fp32 -> one register of two fp16 (round to nearest): .lo = a, .hi = b
+__device__ __forceinline__ uint32_t pack_h2(const float a, const float b) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
 }
-// d (16x8, fp32) = a (16x8, tf32, row) * b (8x8, tf32, col) + c; fragment layout of PTX mma.m16n8k8:
-// a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4); b0 (t, g) b1 (t+4, g); c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
-// with g = lane / 4, t = lane % 4.
+__device__ __forceinline__ float2 unpack_h2(const uint32_t p) {
+    float2 f;
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(p));
+    return f;
+}
+// d (16x8, fp32) = a (16x16, fp16, row) * b (16x8, fp16, col) + c; fragment layout of PTX mma.m16n8k16, g = lane / 4,
+// t = lane % 4: a0 (g, 2t..2t+1) a1 (g+8, 2t..2t+1) a2 (g, 2t+8..2t+9) a3 (g+8, 2t+8..2t+9); b0 (2t..2t+1, g)
+// b1 (2t+8..2t+9, g); c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1).  The contraction index is free to
+// permute: slots (2t, 2t+1, 2t+8, 2t+9) carry the tile's entries (t, t+4, t+8, t+12).
 __device__ __forceinline__ void mma_zero(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
         : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.f));
 }
 __device__ __forceinline__ void mma_acc(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-    asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    asm("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// ---- per-column power-of-two scaling of the factor (exact) ----
+// colmax[c] = max_i |X[i][c]| as the bit pattern of a non-negative float (atomicMax on the bits is order-free)
+__global__ void colscale_max_kernel(const float *__restrict__ X, size_t rows, int k, unsigned *__restrict__ colmax) {
+    const size_t total = rows * (size_t)k;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    // a thread's column is fixed when the stride is a multiple of k: round the stride down to one
+    const size_t step = stride - stride % k;
+    const size_t p0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (p0 >= step) return;
+    float m = 0.f;
+    for (size_t p = p0; p < total; p += step) m = fmaxf(m, fabsf(X[p]));
+    if (m > 0.f) atomicMax(colmax + (p0 % k), __float_as_uint(m));
+}
+// scale[c] = 2^(15 - e) with max = f * 2^e, f in [0.5, 1): the scaled column maximum lies in [2^14, 2^15).
+// Xs = X * scale (exact), invs = 1 / scale.  All-zero / non-finite columns keep scale 1.
+__global__ void colscale_apply_kernel(const float *__restrict__ X, size_t rows, int k, const unsigned *__restrict__ colmax,
+                                      float *__restrict__ Xs, float *__restrict__ invs) {
+    extern __shared__ float sc[];
+    for (int c = threadIdx.x; c < k; c += blockDim.x) {
+        const float m = __uint_as_float(colmax[c]);
+        float s = 1.f;
+        if (m > 0.f && m < 3.0e38f) {
+            int e;
+            frexpf(m, &e);
+            e = 15 - e;
+            e = e > 100 ? 100 : (e < -100 ? -100 : e);
+            s = ldexpf(1.f, e);
+        }
+        sc[c] = s;
+        if (blockIdx.x == 0) invs[c] = 1.f / s;
+    }
+    __syncthreads();
+    const size_t total = rows * (size_t)k;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x)
+        Xs[p] = X[p] * sc[p % k];
 }
 
 // SOLVE = true : F-update -- solve (Gram + lambda I) f = rhs and store the k results in F[j].
 // SOLVE = false: "store" mode used by the X-update (rows = time stamps, X = the series factor): the k x k
 //                Gram (full symmetric square, fp32) goes to Gout[j] and the rhs to F[j]; rows without entries
 //                get zeros.
+// X is the column-scaled factor (colscale_apply_kernel), invs its inverse scales.
 template <int K, int NW, int MINB, bool SOLVE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
-                    const float *__restrict__ X, float *__restrict__ F, float *__restrict__ Gout, double lambda,
-                    uint32_t nseries, unsigned *__restrict__ queue) {
+                    const float *__restrict__ X, const float *__restrict__ invs, float *__restrict__ F,
+                    float *__restrict__ Gout, double lambda, uint32_t nseries, unsigned *__restrict__ queue) {
     typedef Cfg<K> C;
     constexpr int NC = C::NC, MT = C::MT, NT = C::NT, CH = C::CH, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
     constexpr int SF = C::STAGE_FLOATS, ld = C::ld, NTH = NW * 32;
@@ -204,27 +257,27 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                     }
                     const float *tb = st + s_cur * SF;
                     const float *yb = ys + s_cur * ET;
+                    {
+                        const float *p = tb + tig * RS + g;
+                        float y[4];
 #pragma unroll
-                    for (int c8 = 0; c8 < ET / 8; ++c8) {
-                        const float *p = tb + (c8 * 8 + tig) * RS + g;
-                        const float y0 = yb[c8 * 8 + tig], y1 = yb[c8 * 8 + tig + 4];
-                        uint32_t ah[MT][4], al[MT][4], bh[NC][2], bl[NC][2];
+                        for (int q = 0; q < 4; ++q) y[q] = yb[tig + 4 * q];
+                        uint32_t a1[MT][4], a2[MT][4], b1[NC][2], b2[NC][2];   // h1 / h2 parts, A- and B-arranged
 #pragma unroll
                         for (int c = 0; c < 2 * MT; ++c) {
-                            if (c < NC) {
-                                const float v0 = p[8 * c], v1 = p[4 * RS + 8 * c];
-                                racc[c] = fmaf(y0, v0, racc[c]);
-                                racc[c] = fmaf(y1, v1, racc[c]);
-                                uint32_t h0, l0, h1, l1;
-                                split_tf32(v0, h0, l0);
-                                split_tf32(v1, h1, l1);
-                                ah[c >> 1][(c & 1)] = h0; ah[c >> 1][(c & 1) + 2] = h1;
-                                al[c >> 1][(c & 1)] = l0; al[c >> 1][(c & 1) + 2] = l1;
-                                bh[c][0] = h0; bh[c][1] = h1;
-                                bl[c][0] = l0; bl[c][1] = l1;
-                            } else {   // virtual chunk past k (NC odd): zero rows of the last 16-row tile
-                                ah[c >> 1][(c & 1)] = 0u; ah[c >> 1][(c & 1) + 2] = 0u;
-                                al[c >> 1][(c & 1)] = 0u; al[c >> 1][(c & 1) + 2] = 0u;
+#pragma unroll
+                            for (int hh = 0; hh < 2; ++hh) {   // contraction slots 2t..2t+1 (+8): entries (t + 8 hh, t + 8 hh + 4)
+                                uint32_t p1 = 0u, p2 = 0u;     // virtual chunk past k (NC odd): zero rows of the last 16-row tile
+                                if (c < NC) {
+                                    const float x0 = p[(8 * hh) * RS + 8 * c], x1 = p[(8 * hh + 4) * RS + 8 * c];
+                                    racc[c] = fmaf(y[2 * hh], x0, racc[c]);
+                                    racc[c] = fmaf(y[2 * hh + 1], x1, racc[c]);
+                                    p1 = pack_h2(x0, x1);
+                                    const float2 f = unpack_h2(p1);
+                                    p2 = pack_h2(x0 - f.x, x1 - f.y);
+                                    b1[c][hh] = p1; b2[c][hh] = p2;
+                                }
+                                a1[c >> 1][(c & 1) + 2 * hh] = p1; a2[c >> 1][(c & 1) + 2 * hh] = p2;
                             }
                         }
                         int t = 0;
@@ -233,9 +286,9 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
 #pragma unroll
                             for (int nt = 2 * mt; nt < NC; ++nt) {
                                 float d[4];
-                                mma_zero(d, al[mt], bh[nt]);     // small terms first
-                                mma_acc(d, ah[mt], bl[nt]);
-                                mma_acc(d, ah[mt], bh[nt]);
+                                mma_zero(d, a2[mt], b1[nt]);     // small terms first
+                                mma_acc(d, a1[mt], b2[nt]);
+                                mma_acc(d, a1[mt], b1[nt]);
 #pragma unroll
                                 for (int q = 0; q < 4; ++q) acc[t][q] += d[q];
                                 ++t;
@@ -258,13 +311,13 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                 if (r <= c && c < K) {
                     double s = P[u];
                     for (int w = 1; w < nwa; ++w) s += P[(size_t)w * NT * 128 + u];
-                    A[c * ld + r] = s;
+                    A[c * ld + r] = s * ((double)invs[r] * (double)invs[c]);     // undo the column scaling (exact)
                 }
             }
             for (int c = tid; c < K; c += NTH) {
                 double s = R[c];
                 for (int w = 1; w < nwa; ++w) s += R[w * 8 * NC + c];
-                A[K * ld + c] = s;
+                A[K * ld + c] = s * (double)invs[c];
             }
             __syncthreads();
             if (SOLVE) {
@@ -307,9 +360,20 @@ static inline bool f_update_mma_supported(int k) {
 // three 4-warp CTAs per SM.
 template <bool SOLVE>
 static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
-                                      const V *X, V *F, V *Gout, int k, double lambda, uint32_t nseries, unsigned *queue,
-                                      unsigned long long *launches) {
-    if (cudaMemsetAsync(queue, 0, sizeof(unsigned), st) != cudaSuccess) return 1;
+                                      const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
+                                      uint32_t nseries, unsigned *queue, unsigned long long *launches) {
+    // queue[0] = series counter, queue[8 .. 8+k) = per-column max |x| (bit patterns)
+    if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (8 + 128), st) != cudaSuccess) return 1;
+    {
+        const size_t total = xrows * (size_t)k;
+        unsigned g1 = (unsigned)((total + 255) / 256);
+        if (g1 > (unsigned)(4 * num_sms)) g1 = (unsigned)(4 * num_sms);
+        if (g1 == 0) g1 = 1;
+        if ((size_t)g1 * 256 < (size_t)k) g1 = (unsigned)((k + 255) / 256);
+        fm::colscale_max_kernel<<<g1, 256, 0, st>>>(X, xrows, k, queue + 8);
+        fm::colscale_apply_kernel<<<g1, 256, sizeof(float) * k, st>>>(X, xrows, k, queue + 8, Xs, invs);
+        *launches += 2;
+    }
     const bool wide = nseries < (uint32_t)(24 * num_sms);
 #define FM_LAUNCH(KK, NWW, MINBB)                                                                               \
     do {                                                                                                        \
@@ -318,7 +382,7 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
         unsigned grid = (unsigned)(MINBB * num_sms);                                                            \
         if (grid > nseries) grid = nseries;                                                                     \
-        kfn<<<grid ? grid : 1, NWW * 32, smem, st>>>(ptr, idx, val, X, F, Gout, lambda, nseries, queue);        \
+        kfn<<<grid ? grid : 1, NWW * 32, smem, st>>>(ptr, idx, val, Xs, invs, F, Gout, lambda, nseries, queue);        \
     } while (0)
 #define FM_CASE(KK)                                                                                             \
     case KK:                                                                                                    \
@@ -341,6 +405,6 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
 
 static inline bool f_update_mma_supported(int) { return false; }
 template <bool SOLVE>
-static inline int f_update_mma_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, V *, V *, int,
-                                      double, uint32_t, unsigned *, unsigned long long *) { return 1; }
+static inline int f_update_mma_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, V *, float *,
+                                      V *, V *, int, double, uint32_t, unsigned *, unsigned long long *) { return 1; }
 #endif

@@ -113,6 +113,8 @@ struct trmf_b200_session {
     V *part_tk = nullptr;         // this rank's partial of a T x k pass, all-reduced in place
     // X-update through per-time-stamp Grams (fp32 build, k % 4 == 0, k <= 64)
     V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
+    V *Xs = nullptr;                  // column-scaled copy of the factor the mma Gram kernel reads (max(T, n) x k)
+    float *invs = nullptr;            // its k inverse scales
     int gram_state = 0;               // 0 = not decided, 1 = enabled, -1 = disabled
     int prev_cg = -1;                 // CG steps of the previous x_update of this session (-1: none yet)
     bool gram_now = false;            // this x_update goes through the Grams
@@ -272,7 +274,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -445,6 +447,13 @@ static int f_kernel_choice(int k, const V *X) {
     if (!want_ffma && f_update_mma_supported(k)) return F_KERNEL_MMA;
     if (f_update_tiled_supported(k)) return F_KERNEL_FFMA;
     return F_KERNEL_GENERIC;
+}
+
+// scratch of the mma Gram kernel: the column-scaled factor copy and its inverse scales
+static int mma_scratch(S *s) {
+    if (s->Xs) return 0;
+    if (dev_alloc(&s->Xs, std::max(s->T, s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128)) return 1;
+    return 0;
 }
 
 // --------------------------------------------------------------------------
@@ -651,8 +660,9 @@ extern "C" int trmf_b200_f_update(S *s) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
         const int fk = f_kernel_choice(k, s->W);
         if (fk == F_KERNEL_MMA) {
-            if (f_update_mma_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
-                                          s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
+            if (mma_scratch(s)) return 1;
+            if (f_update_mma_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs, s->H,
+                                          (V *)nullptr, k, s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
                 return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (fk == F_KERNEL_FFMA) {
             if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
@@ -726,8 +736,9 @@ extern "C" int trmf_b200_x_update(S *s) {
         if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
             int rc;
             if (f_kernel_choice(s->k, s->H) == F_KERNEL_MMA)
-                rc = f_update_mma_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
-                                                (uint32_t)s->T, s->queue, &s->launches);
+                rc = mma_scratch(s) ||
+                     f_update_mma_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
+                                                s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches);
             else
                 rc = f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
                                                   (uint32_t)s->T, s->queue, &s->launches);
