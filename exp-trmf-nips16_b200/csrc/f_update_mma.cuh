@@ -80,6 +80,13 @@ __device__ __forceinline__ uint32_t pack_h2(const float a, const float b) {
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
     return r;
 }
+// opaque register copy: a value that sits in an A quad AND a B pair needs two homes; hiding the copy from the
+// optimiser gives it exactly one MOV per value instead of a re-pack in front of every HMMA
+__device__ __forceinline__ uint32_t reg_copy(const uint32_t v) {
+    uint32_t r;
+    asm("mov.b32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
 __device__ __forceinline__ float2 unpack_h2(const uint32_t p) {
     float2 f;
     asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(f.x), "=f"(f.y) : "r"(p));
@@ -193,29 +200,37 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                 for (int c = 0; c < NC; ++c) racc[c] = 0.f;
                 bool first = true;
 
-                uint32_t nidx;   // lane e < ET: row index of entry e of the next tile to issue
-                auto load_idx = [&](int i) {
-                    const uint32_t e = (uint32_t)(warp + i * NW) * ET + lane;
-                    nidx = (lane < ET && i < my_tiles && e < nnz) ? __ldg(sidx + e) : 0u;
+                uint32_t nidx;   // lane e (and e + 16): row index of entry e of the next tile to issue
+                auto load_idx = [&](int i) {   // clamped: always a valid address, also one tile past the end
+                    uint32_t e = (uint32_t)(warp + i * NW) * ET + (lane & 15);
+                    e = e < nnz ? e : nnz - 1;
+                    nidx = __ldg(sidx + e);
                 };
                 auto issue = [&](int i, int s) {   // gathers local tile i (indices in nidx) into stage s
                     const uint32_t base = (uint32_t)(warp + i * NW) * ET;
-                    const uint32_t rem = nnz - base;
-                    const int cnt = rem < (uint32_t)ET ? (int)rem : ET;
                     float *dst = st + s * SF;
+                    if (base + ET <= nnz) {        // full tile (warp-uniform): no per-request predicates
 #pragma unroll
-                    for (int q = 0; q < NQ; ++q) {
-                        const int id = q * 32 + lane;
-                        const int e = id / CH, cc = id - e * CH;
-                        const uint32_t row = __shfl_sync(FULL_MASK, nidx, e & 15);
-                        if (id < ET * CH && e < cnt) cp_async16(dst + e * RS + 4 * cc, X + (size_t)row * K + 4 * cc);
-                    }
-                    if (lane < ET) {
+                        for (int q = 0; q < NQ; ++q) {
+                            const int id = q * 32 + lane;
+                            const int e = id / CH, cc = id - e * CH;
+                            const uint32_t row = __shfl_sync(FULL_MASK, nidx, e & 15);
+                            if ((ET * CH) % 32 == 0 || id < ET * CH) cp_async16(dst + e * RS + 4 * cc, X + (size_t)row * K + 4 * cc);
+                        }
+                        if (lane < ET) cp_async4(ys + s * ET + lane, sval + base + lane);
+                    } else {
+                        const int cnt = (int)(nnz - base);
+#pragma unroll
+                        for (int q = 0; q < NQ; ++q) {
+                            const int id = q * 32 + lane;
+                            const int e = id / CH, cc = id - e * CH;
+                            const uint32_t row = __shfl_sync(FULL_MASK, nidx, e & 15);
+                            if (id < ET * CH && e < cnt) cp_async16(dst + e * RS + 4 * cc, X + (size_t)row * K + 4 * cc);
+                        }
                         if (lane < cnt) cp_async4(ys + s * ET + lane, sval + base + lane);
-                        else ys[s * ET + lane] = 0.f;
+                        else if (lane < ET) ys[s * ET + lane] = 0.f;
+                        for (int p = cnt * RS + lane; p < SF; p += 32) dst[p] = 0.f;   // rows past the end read as zero
                     }
-                    if (cnt < ET)   // tail tile: rows past the end must read as zero
-                        for (int p = cnt * RS + lane; p < SF; p += 32) dst[p] = 0.f;
                 };
                 auto flush = [&]() {
 #pragma unroll
@@ -275,7 +290,7 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                                     p1 = pack_h2(x0, x1);
                                     const float2 f = unpack_h2(p1);
                                     p2 = pack_h2(x0 - f.x, x1 - f.y);
-                                    b1[c][hh] = p1; b2[c][hh] = p2;
+                                    b1[c][hh] = reg_copy(p1); b2[c][hh] = reg_copy(p2);
                                 }
                                 a1[c >> 1][(c & 1) + 2 * hh] = p1; a2[c >> 1][(c & 1) + 2 * hh] = p2;
                             }

@@ -15,6 +15,7 @@
 #include "x_pass_fast.cuh"
 #include "lag_update.cuh"
 #include "dense.cuh"
+#include "ingest.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -338,19 +339,27 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) || h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) ||
             h2d_new(s, &s->val, Y->val, s->nnz))
             return 1;
-        // by-time CSR: allocate in stream order, copy on the side stream, publish with an event
         if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->col_idx, s->nnz) || dev_alloc(&s->val_t, s->nnz)) return 1;
-        CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&s->csr_ready, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));                 // the allocations are ordered on s->stream
-        CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
-        CUDA_TRY(cudaMemcpyAsync(s->row_ptr, Y->row_ptr, (s->T + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
-        if (s->nnz) {
-            CUDA_TRY(cudaMemcpyAsync(s->col_idx, Y->col_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
-            CUDA_TRY(cudaMemcpyAsync(s->val_t, Y->val_t, s->nnz * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
+        const bool have_host_csr = Y->row_ptr && (s->nnz == 0 || (Y->col_idx && Y->val_t));
+        if (!have_host_csr || !getenv("TRMF_B200_HOST_CSR")) {
+            // by-time CSR derived in HBM from the by-series CSC just uploaded (ingest.cuh): halves the PCIe traffic
+            CUDA_TRY(csr_from_csc_device<V>(s->stream, s->num_sms, s->T, s->n, s->nnz, s->col_ptr, s->row_idx, s->val, s->row_ptr,
+                                            s->col_idx, s->val_t));
+            s->launches += 5;
+        } else {
+            // caller's CSR arrays as given: copy on the side stream, publish with an event
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->csr_ready, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));                 // the allocations are ordered on s->stream
+            CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
+            CUDA_TRY(cudaMemcpyAsync(s->row_ptr, Y->row_ptr, (s->T + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->copy_stream));
+            if (s->nnz) {
+                CUDA_TRY(cudaMemcpyAsync(s->col_idx, Y->col_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                CUDA_TRY(cudaMemcpyAsync(s->val_t, Y->val_t, s->nnz * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
+            }
+            CUDA_TRY(cudaEventRecord(s->csr_ready, s->copy_stream));
+            s->csr_pending = true;
         }
-        CUDA_TRY(cudaEventRecord(s->csr_ready, s->copy_stream));
-        s->csr_pending = true;
     } else {
         if (h2d_new(s, &s->Yd, Y->val, s->T * s->n)) return 1;
     }
@@ -395,6 +404,47 @@ extern "C" S *trmf_b200_create_device(uint64_t T, uint64_t n, uint64_t nnz, uint
     s->val = (V *)const_cast<void *>(d_val);
     s->W = (V *)d_W; s->H = (V *)d_H; s->th = (V *)d_lag_val;
     return s;
+}
+
+// Host CSC in, host CSR out, through the device transpose (ingest.cuh): the ingest primitive on its own.
+extern "C" int trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *row_idx,
+                                      const void *val, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, int32_t device) {
+    g_last_error.clear();
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (T >= (1ull << 32) || n >= (1ull << 32)) return fail("T and n must fit uint32 indices");
+    cudaStream_t st;
+    CUDA_TRY(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    uint64_t *d_cp = nullptr, *d_rp = nullptr;
+    uint32_t *d_ri = nullptr, *d_ci = nullptr;
+    V *d_v = nullptr, *d_vt = nullptr;
+    const size_t nz = nnz ? nnz : 1;
+    int rc = 0;
+    if (cudaMalloc((void **)&d_cp, (n + 1) * sizeof(uint64_t)) || cudaMalloc((void **)&d_rp, (T + 1) * sizeof(uint64_t)) ||
+        cudaMalloc((void **)&d_ri, nz * sizeof(uint32_t)) || cudaMalloc((void **)&d_ci, nz * sizeof(uint32_t)) ||
+        cudaMalloc((void **)&d_v, nz * sizeof(V)) || cudaMalloc((void **)&d_vt, nz * sizeof(V)))
+        rc = fail("csr_from_csc: out of device memory");
+    if (!rc) {
+        cudaMemcpyAsync(d_cp, col_ptr, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st);
+        if (nnz) {
+            cudaMemcpyAsync(d_ri, row_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, st);
+            cudaMemcpyAsync(d_v, val, nnz * sizeof(V), cudaMemcpyHostToDevice, st);
+        }
+        cudaError_t e = csr_from_csc_device<V>(st, prop.multiProcessorCount, T, n, nnz, d_cp, d_ri, d_v, d_rp, d_ci, d_vt);
+        if (e == cudaSuccess) {
+            cudaMemcpyAsync(row_ptr, d_rp, (T + 1) * sizeof(uint64_t), cudaMemcpyDeviceToHost, st);
+            if (nnz) {
+                cudaMemcpyAsync(col_idx, d_ci, nnz * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+                cudaMemcpyAsync(val_t, d_vt, nnz * sizeof(V), cudaMemcpyDeviceToHost, st);
+            }
+            e = cudaStreamSynchronize(st);
+        }
+        if (e != cudaSuccess) rc = fail("csr_from_csc failed: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_cp); cudaFree(d_rp); cudaFree(d_ri); cudaFree(d_ci); cudaFree(d_v); cudaFree(d_vt);
+    cudaStreamDestroy(st);
+    return rc;
 }
 
 extern "C" int trmf_b200_set_params(S *s, double lambdaI, double lambdaAR, double lambdaLag) {

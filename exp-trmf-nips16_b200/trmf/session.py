@@ -58,6 +58,8 @@ def _lib(dtype):
                                              c_double, c_double, c_uint64, c_int32]
     lib.trmf_b200_free_synth.restype = None
     lib.trmf_b200_free_synth.argtypes = [POINTER(SynthDesc)]
+    lib.trmf_b200_csr_from_csc.argtypes = [c_uint64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_int32]
     lib.trmf_b200_version.restype = ctypes.c_char_p
     lib.trmf_b200_value_bytes.restype = c_int32
     _proto_done.add(id(lib))
@@ -173,3 +175,24 @@ class Session(object):
             self.close()
         except Exception:
             pass
+
+
+def csr_from_csc(csc, dtype=None, device=0):
+    """By-time CSR of a scipy CSC matrix through the device transpose (`trmf_b200_csr_from_csc`):
+    returns (row_ptr uint64[T+1], col_idx uint32[nnz], val_t dtype[nnz]) -- the arrays
+    PyMatrix would otherwise get from a second scipy conversion (reference rf_util.py:88-98)."""
+    dtype = np.dtype(dtype or csc.dtype)
+    lib = _lib(dtype)
+    T, n = csc.shape
+    col_ptr = np.ascontiguousarray(csc.indptr, dtype=np.uint64)
+    row_idx = np.ascontiguousarray(csc.indices, dtype=np.uint32)
+    val = np.ascontiguousarray(csc.data, dtype=dtype)
+    nnz = int(col_ptr[-1])
+    row_ptr = np.empty(T + 1, dtype=np.uint64)
+    col_idx = np.empty(nnz, dtype=np.uint32)
+    val_t = np.empty(nnz, dtype=dtype)
+    rc = lib.trmf_b200_csr_from_csc(T, n, nnz, col_ptr.ctypes.data, row_idx.ctypes.data, val.ctypes.data,
+                                    row_ptr.ctypes.data, col_idx.ctypes.data, val_t.ctypes.data, device)
+    if rc != 0:
+        raise RuntimeError(lib.trmf_b200_last_error().decode())
+    return row_ptr, col_idx, val_t

@@ -173,6 +173,15 @@ void trmf_b200_free_synth(trmf_b200_synth *s);
 /* plain cudaMemcpy device -> host (so that host programs need no CUDA binding of their own) */
 int  trmf_b200_copy_to_host(void *dst_host, const void *src_device, uint64_t bytes);
 
+/* Ingest primitive (replaces the second scipy conversion of reference rf_util.py:88-98): the by-time CSR of Y
+ * (row_ptr u64[T+1], col_idx u32[nnz], val_t ValueType[nnz]) from its by-series CSC (col_ptr u64[n+1], row_idx
+ * u32[nnz], val ValueType[nnz]) by a stable device sort; host arrays in, host arrays out, bit-identical to
+ * scipy's csc.tocsr().  c_trmf_train / trmf_b200_create use the same transpose internally and upload only the
+ * CSC half of a sparse PyMatrix (row_ptr / col_idx / val_t may then be NULL); TRMF_B200_HOST_CSR=1 makes them
+ * upload the caller's CSR arrays instead. */
+int  trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *row_idx,
+                            const void *val, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, int32_t device);
+
 #ifdef __cplusplus
 }
 #endif
