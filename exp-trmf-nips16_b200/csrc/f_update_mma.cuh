@@ -50,12 +50,16 @@ template <int K> struct Cfg {
     static constexpr int NT = ntiles_();            // upper-triangle 16x8 tiles (mt, nt), nt >= 2 mt
     static constexpr int CH = K / 4;                // 16-byte pieces of a factor row
     static constexpr int RS = (NC & 1) ? 8 * NC : 8 * NC + 8;   // staging row stride: >= 8 NC and = 8 (mod 16)
-    static constexpr int STAGES = 3;
+    static constexpr int STAGES = K <= 48 ? 3 : 2;  // a warp spends >1000 clk on a tile: two stages already cover L2 latency
     static constexpr int NQ = (ET * CH + 31) / 32;  // warp-wide LDGSTS per tile
     static constexpr int STAGE_FLOATS = ET * RS;
     static constexpr int ld = K + 1;
     static constexpr size_t a_bytes = sizeof(double) * ((size_t)(K + 1) * (K + 1) + K);
-    static constexpr size_t part_bytes(int nw) { return sizeof(double) * (size_t)nw * (NT * 128 + 8 * NC); }
+    // per-warp fp64 partial in fragment layout: 4 x 32 values per tile, but the first tile of every 16-row group
+    // (nt = 2 mt) only keeps its upper 8 rows -- rows g+8 there lie below the diagonal
+    static constexpr int PW = NT * 128 - MT * 64;
+    __host__ __device__ static constexpr int poff(int mt, int tin) { int t = tin; for (int m = 0; m < mt; ++m) t += NC - 2 * m; return 128 * t - 64 * (mt + (tin > 0 ? 1 : 0)); }
+    static constexpr size_t part_bytes(int nw) { return sizeof(double) * (size_t)nw * (PW + 8 * NC); }
     static constexpr size_t stage_bytes(int nw) {
         const size_t s = sizeof(float) * (size_t)nw * STAGES * (STAGE_FLOATS + ET);
         return ((s > a_bytes ? s : a_bytes) + 15) & ~(size_t)15;
@@ -158,9 +162,10 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
     constexpr int NC = C::NC, MT = C::MT, NT = C::NT, CH = C::CH, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
     constexpr int SF = C::STAGE_FLOATS, ld = C::ld, NTH = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *P = reinterpret_cast<double *>(smem_raw);                 // [NW][NT*128]  per-warp Gram partials (fragment layout)
-    double *R = P + (size_t)NW * NT * 128;                            // [NW][8*NC]    per-warp rhs partials
-    constexpr size_t PART_BYTES = sizeof(double) * (size_t)NW * (NT * 128 + 8 * NC);
+    constexpr int PW = C::PW;
+    double *P = reinterpret_cast<double *>(smem_raw);                 // [NW][PW]      per-warp Gram partials (fragment layout)
+    double *R = P + (size_t)NW * PW;                                  // [NW][8*NC]    per-warp rhs partials
+    constexpr size_t PART_BYTES = sizeof(double) * (size_t)NW * (PW + 8 * NC);
     float *stage = reinterpret_cast<float *>(smem_raw + PART_BYTES);   // [NW][STAGES][ET*RS]
     float *ystage = stage + (size_t)NW * STAGES * SF;                 // [NW][STAGES][ET]
     double *A = reinterpret_cast<double *>(stage);                    // epilogue only: (K+1) x ld lower triangle + rhs row
@@ -177,7 +182,7 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
 
     float *st = stage + (size_t)warp * STAGES * SF;
     float *ys = ystage + (size_t)warp * STAGES * ET;
-    double *Pw = P + (size_t)warp * NT * 128;
+    double *Pw = P + (size_t)warp * PW;
     double *Rw = R + (size_t)warp * 8 * NC;
 
     while (j < nseries) {
@@ -233,14 +238,23 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                     }
                 };
                 auto flush = [&]() {
+                    {
+                        int t = 0;
 #pragma unroll
-                    for (int t = 0; t < NT; ++t)
+                        for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            double *d = Pw + (t * 4 + q) * 32 + lane;
-                            *d = first ? (double)acc[t][q] : *d + (double)acc[t][q];
-                            acc[t][q] = 0.f;
-                        }
+                            for (int nt = 2 * mt; nt < NC; ++nt) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) {
+                                    if (nt > 2 * mt || q < 2) {
+                                        double *d = Pw + C::poff(mt, nt - 2 * mt) + q * 32 + lane;
+                                        *d = first ? (double)acc[t][q] : *d + (double)acc[t][q];
+                                    }
+                                    acc[t][q] = 0.f;
+                                }
+                                ++t;
+                            }
+                    }
 #pragma unroll
                     for (int c = 0; c < NC; ++c) {
                         float r = racc[c];
@@ -323,9 +337,10 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                 const int nt = 2 * mt + t;
                 const int q = (u >> 5) & 3, l = u & 31;
                 const int r = 16 * mt + (l >> 2) + 8 * (q >> 1), c = 8 * nt + 2 * (l & 3) + (q & 1);
-                if (r <= c && c < K) {
-                    double s = P[u];
-                    for (int w = 1; w < nwa; ++w) s += P[(size_t)w * NT * 128 + u];
+                if (r <= c && c < K) {     // (r <= c excludes the slots the partials do not store)
+                    const int pu = 128 * (u >> 7) - 64 * (mt + (t > 0 ? 1 : 0)) + (q * 32 + l);
+                    double s = P[pu];
+                    for (int w = 1; w < nwa; ++w) s += P[(size_t)w * PW + pu];
                     A[c * ld + r] = s * ((double)invs[r] * (double)invs[c]);     // undo the column scaling (exact)
                 }
             }
@@ -367,7 +382,7 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
 }   // namespace fm
 
 static inline bool f_update_mma_supported(int k) {
-    switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: return true; }
+    switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: case 56: case 60: case 64: return true; }
     return false;
 }
 
@@ -407,6 +422,15 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
         FM_CASE(8) FM_CASE(16) FM_CASE(20) FM_CASE(24) FM_CASE(32) FM_CASE(40)
         case 48:   // 12 accumulator tiles: 23.5 KB of shared memory per warp -> 8 warps per SM
             if (wide) FM_LAUNCH(48, 8, 1); else FM_LAUNCH(48, 4, 2);
+            break;
+        case 56:   // 16 / 20 accumulator tiles: 8 warps per SM
+            if (wide) FM_LAUNCH(56, 8, 1); else FM_LAUNCH(56, 4, 2);
+            break;
+        case 60:
+            if (wide) FM_LAUNCH(60, 8, 1); else FM_LAUNCH(60, 4, 2);
+            break;
+        case 64:
+            if (wide) FM_LAUNCH(64, 8, 1); else FM_LAUNCH(64, 4, 2);
             break;
         default: return 1;
     }
