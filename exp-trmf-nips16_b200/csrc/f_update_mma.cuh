@@ -28,7 +28,7 @@
 //    -1.1e-6 bias).
 //
 // Work decomposition: CTA = NW warps, one series at a time (atomic queue).  The series' entries are cut into
-// tiles of 16; warp w takes tiles w, w + NW, ...  Each warp runs its own 3-stage cp.async (LDGSTS) pipeline
+// tiles of 16; warp w takes tiles w, w + NW, ...  Each warp runs its own 2-stage cp.async (LDGSTS) pipeline
 // (16 factor rows of k floats per stage, the Y values ride along with 4-byte copies) -- no CTA barrier inside
 // a series.  Fragment loads are bank-conflict free because the staging row stride RS = 8 (mod 16) floats.
 // At the end of a series the NW fp64 partials are added in warp order (bitwise reproducible), the scaling is
@@ -50,7 +50,7 @@ template <int K> struct Cfg {
     static constexpr int NT = ntiles_();            // upper-triangle 16x8 tiles (mt, nt), nt >= 2 mt
     static constexpr int CH = K / 4;                // 16-byte pieces of a factor row
     static constexpr int RS = (NC & 1) ? 8 * NC : 8 * NC + 8;   // staging row stride: >= 8 NC and = 8 (mod 16)
-    static constexpr int STAGES = K <= 48 ? 3 : 2;  // a warp spends >1000 clk on a tile: two stages already cover L2 latency
+    static constexpr int STAGES = 2;               // a warp spends ~1000 clk on a tile: two stages already cover L2 latency  // a warp spends >1000 clk on a tile: two stages already cover L2 latency
     static constexpr int NQ = (ET * CH + 31) / 32;  // warp-wide LDGSTS per tile
     static constexpr int STAGE_FLOATS = ET * RS;
     static constexpr int ld = K + 1;
@@ -386,8 +386,9 @@ static inline bool f_update_mma_supported(int k) {
     return false;
 }
 
-// returns 0 on success.  `wide` selects one 12-warp CTA per SM (few series: finer load balance) instead of
-// three 4-warp CTAs per SM.
+// returns 0 on success.  `wide` selects one 16-warp CTA per SM (few series: finer load balance) instead of
+// four 4-warp CTAs per SM (16 warps at 128 registers; measured 3.20 ms against 3.50 ms for 3 x 4 warps at 168
+// registers at C2 -- with the issue port held 8 clk per HMMA, more resident warps is what hides the rest).
 template <bool SOLVE>
 static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
                                       const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
@@ -416,12 +417,12 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
     } while (0)
 #define FM_CASE(KK)                                                                                             \
     case KK:                                                                                                    \
-        if (wide) FM_LAUNCH(KK, 12, 1); else FM_LAUNCH(KK, 4, 3);                                               \
+        if (wide) FM_LAUNCH(KK, 16, 1); else FM_LAUNCH(KK, 4, 4);                                               \
         break;
     switch (k) {
         FM_CASE(8) FM_CASE(16) FM_CASE(20) FM_CASE(24) FM_CASE(32) FM_CASE(40)
-        case 48:   // 12 accumulator tiles: 23.5 KB of shared memory per warp -> 8 warps per SM
-            if (wide) FM_LAUNCH(48, 8, 1); else FM_LAUNCH(48, 4, 2);
+        case 48:   // 12 accumulator tiles: 18 KB of shared memory per warp -> 12 warps per SM
+            if (wide) FM_LAUNCH(48, 12, 1); else FM_LAUNCH(48, 4, 3);
             break;
         case 56:   // 16 / 20 accumulator tiles: 8 warps per SM
             if (wide) FM_LAUNCH(56, 8, 1); else FM_LAUNCH(56, 4, 2);
