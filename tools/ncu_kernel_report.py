@@ -11,7 +11,9 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_tensor.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
         "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "sm__cycles_elapsed.max", "lts__t_sectors_op_read.sum",
-        "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum"]
+        "smsp__inst_executed_op_local_ld.sum", "smsp__inst_executed_op_local_st.sum",
+        "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg"]
 
 
 def run(args):
@@ -24,8 +26,9 @@ def main(path):
     for r in rows[2:]:
         print("==", r[hdr.index("Kernel Name")][:90])
         for w in WANT:
-            if w in hdr:
-                print("  {:70s} {} {}".format(w, r[hdr.index(w)], rows[1][hdr.index(w)]))
+            hit = [i for i, n in enumerate(hdr) if n == w or n.endswith("." + w)]
+            if hit:
+                print("  {:70s} {} {}".format(w, r[hit[0]], rows[1][hit[0]]))
     src = list(csv.reader(io.StringIO(run([path, "--page", "source", "--csv"]))))
     starts = [i for i, r in enumerate(src) if r and r[0] == "Kernel Name"]
     for si, st in enumerate(starts):
