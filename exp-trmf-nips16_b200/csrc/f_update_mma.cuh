@@ -148,17 +148,24 @@ __global__ void colscale_apply_kernel(const float *__restrict__ X, size_t rows, 
         Xs[p] = X[p] * sc[p % k];
 }
 
-// SOLVE = true : F-update -- solve (Gram + lambda I) f = rhs and store the k results in F[j].
-// SOLVE = false: "store" mode used by the X-update (rows = time stamps, X = the series factor): the k x k
-//                Gram (full symmetric square, fp32) goes to Gout[j] and the rhs to F[j]; rows without entries
-//                get zeros.
+// MODE_SOLVE : F-update -- solve (Gram + lambda I) f = rhs and store the k results in F[j].
+// MODE_STORE : "store" mode used by the X-update (rows = time stamps, X = the series factor): the k x k
+//              Gram (full symmetric square, fp32) goes to Gout[j] and the rhs to F[j]; rows without entries
+//              get zeros.
+// MODE_GRAD  : MODE_STORE, and the same gather also evaluates the sparse loss at the point Wv (arr_ls_pY_IX::fun
+//              and ::grad, trmf.cpp:231-267): per entry z = <Wv_j, x_e> - Y_je (fp32 dot), F[j] (+)= sum_e z x_e
+//              (fp32 FMAs, fp64 every 128 entries) and frow[j] = sum_e z^2 (fp64) -- the X-update then needs no
+//              separate walk over Omega for fun(w) / grad(w).
 // X is the column-scaled factor (colscale_apply_kernel), invs its inverse scales.
-template <int K, int NW, int MINB, bool SOLVE>
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+template <int K, int NW, int MINB, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
                     const float *__restrict__ X, const float *__restrict__ invs, float *__restrict__ F,
-                    float *__restrict__ Gout, double lambda, uint32_t nseries, unsigned *__restrict__ queue) {
+                    float *__restrict__ Gout, double lambda, uint32_t nseries, unsigned *__restrict__ queue,
+                    const float *__restrict__ Wv, int gaccum, double *__restrict__ frow) {
     typedef Cfg<K> C;
+    constexpr bool SOLVE = MODE == MODE_SOLVE, GRAD = MODE == MODE_GRAD;
     constexpr int NC = C::NC, MT = C::MT, NT = C::NT, CH = C::CH, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
     constexpr int SF = C::STAGE_FLOATS, ld = C::ld, NTH = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -171,6 +178,7 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
     double *A = reinterpret_cast<double *>(stage);                    // epilogue only: (K+1) x ld lower triangle + rhs row
     double *dinv = A + (size_t)(K + 1) * ld;
     __shared__ unsigned next_series;
+    __shared__ double fwarp[NW];                                      // MODE_GRAD: per-warp sum of squared residuals
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, tig = lane & 3;
@@ -204,6 +212,13 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
 #pragma unroll
                 for (int c = 0; c < NC; ++c) racc[c] = 0.f;
                 bool first = true;
+                float wl[NC];          // MODE_GRAD: this lane's columns of the point, pre-divided by the column scales
+                double fsum = 0.0;
+                if (GRAD) {
+#pragma unroll
+                    for (int c = 0; c < NC; ++c)
+                        wl[c] = (g + 8 * c < K) ? __ldg(Wv + (size_t)j * K + g + 8 * c) * __ldg(invs + g + 8 * c) : 0.f;
+                }
 
                 uint32_t nidx;   // lane e (and e + 16): row index of entry e of the next tile to issue
                 auto load_idx = [&](int i) {   // clamped: always a valid address, also one tile past the end
@@ -288,9 +303,30 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                     const float *yb = ys + s_cur * ET;
                     {
                         const float *p = tb + tig * RS + g;
-                        float y[4];
+                        float y[4];   // weights of the tile's entries (t, t+4, t+8, t+12) in the rhs sum: Y, or the residual
 #pragma unroll
                         for (int q = 0; q < 4; ++q) y[q] = yb[tig + 4 * q];
+                        if (GRAD) {
+                            float z[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                z[q] = 0.f;
+#pragma unroll
+                                for (int c = 0; c < NC; ++c) z[q] = fmaf(wl[c], p[(4 * q) * RS + 8 * c], z[q]);
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {   // fold the 8 lanes that share entry t + 4q (same bits on every lane)
+                                z[q] += __shfl_xor_sync(FULL_MASK, z[q], 4);
+                                z[q] += __shfl_xor_sync(FULL_MASK, z[q], 8);
+                                z[q] += __shfl_xor_sync(FULL_MASK, z[q], 16);
+                            }
+                            if (g == 0) {
+#pragma unroll
+                                for (int q = 0; q < 4; ++q) { const double rr = (double)y[q] - (double)z[q]; fsum += rr * rr; }
+                            }
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) y[q] = z[q] - y[q];   // rows past the end: x = 0, Y = 0 -> 0
+                        }
                         uint32_t a1[MT][4], a2[MT][4], b1[NC][2], b2[NC][2];   // h1 / h2 parts, A- and B-arranged
 #pragma unroll
                         for (int c = 0; c < 2 * MT; ++c) {
@@ -328,6 +364,11 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                 }
                 cp_async_wait<0>();
                 if (first || my_tiles % FLUSH != 0) flush();
+                if (GRAD) {
+                    fsum += __shfl_xor_sync(FULL_MASK, fsum, 1);
+                    fsum += __shfl_xor_sync(FULL_MASK, fsum, 2);
+                    if (lane == 0) fwarp[warp] = fsum;
+                }
             }
             __syncthreads();   // all partials written, all staging reads done: the staging area becomes A
             // ---- reduce the per-warp partials (warp order) into the lower triangle of A + rhs row ----
@@ -360,7 +401,17 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                     const int r = p / K, c = p - r * K;
                     Gj[p] = (float)(r >= c ? A[r * ld + c] : A[c * ld + r]);
                 }
-                if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
+                if (GRAD) {
+                    if (tid < K) {
+                        float *o = F + (size_t)j * K + tid;
+                        *o = gaccum ? (float)((double)*o + A[K * ld + tid]) : (float)A[K * ld + tid];
+                    }
+                    if (tid == 0) {
+                        double fs = fwarp[0];
+                        for (int w = 1; w < nwa; ++w) fs += fwarp[w];
+                        frow[j] = fs;
+                    }
+                } else if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
             }
             if (RS > K) {   // A overwrote the staging area: padding columns must read as zero again
                 __syncthreads();
@@ -370,13 +421,23 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
         } else if (!SOLVE) {
             float *Gj = Gout + (size_t)j * K * K;
             for (int p = tid; p < K * K; p += NTH) Gj[p] = 0.f;
-            if (tid < K) F[(size_t)j * K + tid] = 0.f;
+            if (GRAD) { if (tid == 0) frow[j] = 0.0; if (!gaccum && tid < K) F[(size_t)j * K + tid] = 0.f; }
+            else if (tid < K) F[(size_t)j * K + tid] = 0.f;
         }
         __syncthreads();
         if (tid == 0) next_series = atomicAdd(queue, 1u);
         __syncthreads();
         j = next_series;
     }
+}
+
+// out = scale * sum_i v[i], deterministic two-level fp64 sum (MODE_GRAD's per-row losses -> the objective's loss part)
+__global__ void sum_rows_kernel(const double *__restrict__ v, size_t n, double scale, double *part, unsigned *ticket, double *out) {
+    __shared__ double red[32];
+    double a = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) a += v[p];
+    a = block_sum(a, red);
+    grid_sum_commit(a, part, ticket, out, scale, red);
 }
 
 }   // namespace fm
@@ -389,10 +450,11 @@ static inline bool f_update_mma_supported(int k) {
 // returns 0 on success.  `wide` selects one 16-warp CTA per SM (few series: finer load balance) instead of
 // four 4-warp CTAs per SM (16 warps at 128 registers; measured 3.20 ms against 3.50 ms for 3 x 4 warps at 168
 // registers at C2 -- with the issue port held 8 clk per HMMA, more resident warps is what hides the rest).
-template <bool SOLVE>
+template <int MODE>
 static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
                                       const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
-                                      uint32_t nseries, unsigned *queue, unsigned long long *launches) {
+                                      uint32_t nseries, unsigned *queue, unsigned long long *launches,
+                                      const V *Wv = nullptr, int gaccum = 0, double *frow = nullptr) {
     // queue[0] = series counter, queue[8 .. 8+k) = per-column max |x| (bit patterns)
     if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (8 + 128), st) != cudaSuccess) return 1;
     {
@@ -409,11 +471,11 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
 #define FM_LAUNCH(KK, NWW, MINBB)                                                                               \
     do {                                                                                                        \
         const size_t smem = fm::Cfg<KK>::smem(NWW);                                                             \
-        auto kfn = fm::f_update_mma_kernel<KK, NWW, MINBB, SOLVE>;                                              \
+        auto kfn = fm::f_update_mma_kernel<KK, NWW, MINBB, MODE>;                                              \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
         unsigned grid = (unsigned)(MINBB * num_sms);                                                            \
         if (grid > nseries) grid = nseries;                                                                     \
-        kfn<<<grid ? grid : 1, NWW * 32, smem, st>>>(ptr, idx, val, Xs, invs, F, Gout, lambda, nseries, queue);        \
+        kfn<<<grid ? grid : 1, NWW * 32, smem, st>>>(ptr, idx, val, Xs, invs, F, Gout, lambda, nseries, queue, Wv, gaccum, frow);        \
     } while (0)
 #define FM_CASE(KK)                                                                                             \
     case KK:                                                                                                    \
@@ -444,7 +506,12 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
 #else   // float64 build: the generic kernel (fp64 FMAs) is the parity path
 
 static inline bool f_update_mma_supported(int) { return false; }
-template <bool SOLVE>
+namespace fm {
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+__global__ void sum_rows_kernel(const double *, size_t, double, double *, unsigned *, double *) {}
+}
+template <int MODE>
 static inline int f_update_mma_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, V *, float *,
-                                      V *, V *, int, double, uint32_t, unsigned *, unsigned long long *) { return 1; }
+                                      V *, V *, int, double, uint32_t, unsigned *, unsigned long long *, const V * = nullptr, int = 0,
+                                      double * = nullptr) { return 1; }
 #endif

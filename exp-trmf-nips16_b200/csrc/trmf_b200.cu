@@ -116,6 +116,7 @@ struct trmf_b200_session {
     V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
     V *Xs = nullptr;                  // column-scaled copy of the factor the mma Gram kernel reads (max(T, n) x k)
     float *invs = nullptr;            // its k inverse scales
+    double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     int gram_state = 0;               // 0 = not decided, 1 = enabled, -1 = disabled
     int prev_cg = -1;                 // CG steps of the previous x_update of this session (-1: none yet)
     bool gram_now = false;            // this x_update goes through the Grams
@@ -275,7 +276,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->frow);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -502,7 +503,7 @@ static int f_kernel_choice(int k, const V *X) {
 // scratch of the mma Gram kernel: the column-scaled factor copy and its inverse scales
 static int mma_scratch(S *s) {
     if (s->Xs) return 0;
-    if (dev_alloc(&s->Xs, std::max(s->T, s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128)) return 1;
+    if (dev_alloc(&s->Xs, std::max(s->T, s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->frow, s->T)) return 1;
     return 0;
 }
 
@@ -711,7 +712,7 @@ extern "C" int trmf_b200_f_update(S *s) {
         const int fk = f_kernel_choice(k, s->W);
         if (fk == F_KERNEL_MMA) {
             if (mma_scratch(s)) return 1;
-            if (f_update_mma_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs, s->H,
+            if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs, s->H,
                                           (V *)nullptr, k, s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
                 return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (fk == F_KERNEL_FFMA) {
@@ -783,18 +784,40 @@ extern "C" int trmf_b200_x_update(S *s) {
         // it pays off from ~4 CG steps on; the previous X-update's step count is the predictor (ALS needs fewer and
         // fewer CG steps as it converges).  TRMF_B200_FORCE_GRAM_HV pins the choice for tests.
         s->gram_now = s->gram_state == 1 && (s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
+        bool fused = false;   // fun(w), grad(w) came out of the Gram build's own gather
         if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
             int rc;
-            if (f_kernel_choice(s->k, s->H) == F_KERNEL_MMA)
-                rc = mma_scratch(s) ||
-                     f_update_mma_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
-                                                s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches);
-            else
+            if (f_kernel_choice(s->k, s->H) == F_KERNEL_MMA) {
+                fused = !getenv("TRMF_B200_NO_FUSED_GRAD");
+                rc = mma_scratch(s);
+                if (!rc && fused) {
+                    // base value + base gradient first (the fused kernel adds the loss gradient on top of g)
+                    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->T, s->k);
+                    LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, s->W, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
+                    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR);
+                    const bool one = s->world == 1;
+                    rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
+                                                            one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
+                                                            s->W, one ? 1 : 0, s->frow);
+                    if (!rc) {
+                        LAUNCH(s, fm::sum_rows_kernel, ew_grid(s, s->T), 256, 0, s->frow, s->T, 0.5, s->part, s->ticket, s->scal + SC_FLOSS);
+                        if (!one) {
+                            if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
+                            if (dist_allreduce_f64(s, s->scal + SC_FLOSS, 1)) return 1;
+                            LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, s->g, 1.0, s->part_tk, 0.0, (const V *)nullptr, s->g, tk);
+                        }
+                    }
+                } else if (!rc) {
+                    rc = f_update_mma_launch<fm::MODE_STORE>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs,
+                                                             s->invs, s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches);
+                }
+            } else {
                 rc = f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
                                                   (uint32_t)s->T, s->queue, &s->launches);
+            }
             if (rc) return fail("gram build launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         }
-        if (fun_grad_launch(s, s->W, s->g)) return 1;
+        if (!fused && fun_grad_launch(s, s->W, s->g)) return 1;
     } else {
         if (fun_launch(s, s->W)) return 1;
         if (grad_launch(s, s->W, s->g)) return 1;
