@@ -212,11 +212,13 @@ def test_python_surface_end_to_end():
 
 
 @pytest.mark.parametrize("env", [{"TRMF_B200_GENERIC_F": "1"}, {"TRMF_B200_NO_GRAM_HV": "1"}, {"TRMF_B200_GENERIC_PASS": "1"},
-                                 {"TRMF_B200_FORCE_GRAM_HV": "1"},
+                                 {"TRMF_B200_FORCE_GRAM_HV": "1"}, {"TRMF_B200_F_KERNEL": "ffma"}, {"TRMF_B200_F_KERNEL": "mma"},
+                                 {"TRMF_B200_NO_FUSED_GRAD": "1"}, {"TRMF_B200_F_KERNEL": "ffma", "TRMF_B200_FORCE_GRAM_HV": "1"},
+                                 {"TRMF_B200_FORCE_GRAM_HV": "1", "TRMF_B200_NO_FUSED_GRAD": "1"},
                                  {"TRMF_B200_GENERIC_F": "1", "TRMF_B200_NO_GRAM_HV": "1", "TRMF_B200_GENERIC_PASS": "1"}])
 def test_float32_kernel_variants_agree(env, monkeypatch):
-    """Every fp32 kernel variant (tiled / generic F kernel, Gram-based / direct Hv, fast / generic walk over
-    Omega) stays within the 1e-5 bar of the float64 oracle, over two outer iterations each started from the
+    """Every fp32 kernel variant (mma / FFMA-tiled / generic Gram kernel, Gram-based / direct Hv, gradient fused
+    into the Gram build or from its own walk, fast / generic walk over Omega) stays within the 1e-5 bar of the float64 oracle, over two outer iterations each started from the
     oracle's factors (so the adaptive Gram/direct choice of the second X-update is exercised too)."""
     for name, value in env.items():
         monkeypatch.setenv(name, value)
@@ -240,4 +242,64 @@ def test_float32_kernel_variants_agree(env, monkeypatch):
         assert int(s.stat("cg_iters")) == info["cg_iter"]
         assert cases.rel(Hg, Ho) < TOL32 and cases.rel(Wg, Wo) < TOL32 and cases.rel(Lg, Lo) < TOL32
         W, H, L = Wo, Ho, Lo
+    s.close()
+
+
+@pytest.mark.parametrize("k", [8, 16, 20, 24, 32, 40, 48, 56, 60, 64])
+def test_mma_gram_kernel_every_rank_ragged_and_badly_scaled(k, monkeypatch):
+    """The split-fp16 mma.sync Gram kernel (csrc/f_update_mma.cuh) at every rank it is compiled for, on a ragged
+    problem (series / time stamps with 0, 1, 15, 16, 17, 33 and many entries: tail tiles, warps without a tile):
+    one F-update and one X-update (Gram build with the fused gradient) against the float64 oracle on the fp32-rounded
+    inputs, F rows bit-for-bit reproducible.  Then the same F-update with factor columns spanning eight orders of
+    magnitude, which the per-column power-of-two scaling in front of the fp16 split has to absorb; there only the
+    well-determined series (>= 2k observations) are held to the bar -- an under-determined row's system
+    (Gram + lambda I with |Gram| / lambda ~ 1e8) is beyond ANY fp32 Gram, the reference's float build included."""
+    monkeypatch.setenv("TRMF_B200_F_KERNEL", "mma")
+    monkeypatch.setenv("TRMF_B200_FORCE_GRAM_HV", "1")
+    from trmf.session import Session
+    T, n = 420, 300
+    rng = np.random.RandomState(700 + k)
+    p = cases.make_problem(T, n, k, [1, 3, 8], 0.5, seed=900 + k)
+    mask = p["mask"].copy()
+    for j, cnt in enumerate([0, 1, 15, 16, 17, 33]):           # ragged series (kept clear of the ragged time stamps)
+        mask[:, 10 + j] = False
+        mask[30 + rng.choice(T - 30, cnt, replace=False), 10 + j] = True
+    for i, cnt in enumerate([0, 1, 15, 16, 17, 33]):           # ragged time stamps (rows of the Gram build)
+        mask[20 + i, :] = False
+        mask[20 + i, 20 + rng.choice(n - 20, cnt, replace=False)] = True
+    f32 = lambda a: np.asarray(a, dtype=np.float32)
+    Y = sps.csr_matrix(f32(np.where(mask, p["Y"], 0.0)))
+    Y64 = Y.astype(np.float64)
+    assert Y[:, 10].nnz == 0 and Y[:, 11].nnz == 1 and Y[20].nnz == 0 and Y[21].nnz == 1
+    lam = (0.5, 5.0, 0.5)
+    W, H, L = (f32(p[x]).astype(np.float64) for x in ("W0", "H0", "L0"))
+    s = Session(Y, p["lags"], f32(W), f32(H), f32(L), missing=True, dtype=np.float32, lambdaI=lam[0], lambdaAR=lam[1], lambdaLag=lam[2])
+    s.f_update()
+    _, Hg, _ = s.download()
+    Ho = tn.f_update_sparse(sps.csc_matrix(Y64), W, H, lam[0])
+    assert np.isfinite(Hg).all() and cases.rel(Hg, Ho) < TOL32
+    assert np.array_equal(Hg[10], f32(H[10]))                  # the series without observations keeps its row
+    s.upload(H=f32(H))
+    s.f_update()
+    _, Hg2, _ = s.download()
+    assert np.array_equal(Hg, Hg2)
+    # X-update from the oracle's F (so both sides start from the same point)
+    s.upload(H=f32(Ho))
+    Ho32 = f32(Ho).astype(np.float64)
+    s.x_update()
+    Wg, _, _ = s.download()
+    info = {}
+    Wo = tn.x_update(tn.SparseLoss(Y64, Ho32), W, p["lags"].astype(np.int64), L, lam[0], lam[1], info)
+    assert int(s.stat("cg_iters")) == info["cg_iter"] and bool(s.stat("accepted")) == info["accepted"]
+    assert abs(s.stat("f") - info["f"]) <= 2e-6 * abs(info["f"])
+    assert cases.rel(Wg, Wo) < TOL32
+    # badly scaled latent dimensions
+    colscale = 10.0 ** rng.uniform(-4, 4, size=k)
+    Ws = f32(p["W0"] * colscale).astype(np.float64)
+    s.upload(W=f32(Ws), H=f32(H))
+    s.f_update()
+    _, Hs, _ = s.download()
+    Hso = tn.f_update_sparse(sps.csc_matrix(Y64), Ws, H, lam[0])
+    well = np.asarray(mask.sum(axis=0)).ravel() >= 2 * k
+    assert well.sum() > n // 2 and cases.rel(Hs[well], Hso[well]) < TOL32
     s.close()
