@@ -454,10 +454,11 @@ template <int MODE>
 static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const V *val,
                                       const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
                                       uint32_t nseries, unsigned *queue, unsigned long long *launches,
-                                      const V *Wv = nullptr, int gaccum = 0, double *frow = nullptr) {
-    // queue[0] = series counter, queue[8 .. 8+k) = per-column max |x| (bit patterns)
-    if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (8 + 128), st) != cudaSuccess) return 1;
-    {
+                                      const V *Wv = nullptr, int gaccum = 0, double *frow = nullptr, bool rescale = true) {
+    // queue[0] = series counter, queue[8 .. 8+k) = per-column max |x| (bit patterns).  rescale = false: Xs / invs are
+    // still valid from the previous launch over the same factor (series-slab launches of one F-update).
+    if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (rescale ? 8 + 128 : 1), st) != cudaSuccess) return 1;
+    if (rescale) {
         const size_t total = xrows * (size_t)k;
         unsigned g1 = (unsigned)((total + 255) / 256);
         if (g1 > (unsigned)(4 * num_sms)) g1 = (unsigned)(4 * num_sms);
@@ -513,5 +514,5 @@ __global__ void sum_rows_kernel(const double *, size_t, double, double *, unsign
 template <int MODE>
 static inline int f_update_mma_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, V *, float *,
                                       V *, V *, int, double, uint32_t, unsigned *, unsigned long long *, const V * = nullptr, int = 0,
-                                      double * = nullptr) { return 1; }
+                                      double * = nullptr, bool = true) { return 1; }
 #endif

@@ -67,6 +67,12 @@ struct trmf_b200_session {
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t csr_ready = nullptr;
     bool csr_pending = false;
+    // host-buffer sessions with a device-built CSR: the CSC arrives in nnz-balanced series slabs on the copy stream;
+    // the first F-update starts on slab b as soon as it has landed (slab_ev[b]), the CSR is built once all have
+    std::vector<size_t> slab_j;          // slab b = series [slab_j[b], slab_j[b+1])
+    std::vector<cudaEvent_t> slab_ev;
+    bool slabs_pending = false;          // the F-update has not consumed the slab events yet
+    bool csr_deferred = false;           // the device transpose has not been issued yet
 
     size_t T = 0, n = 0, nnz = 0;
     int k = 0, L = 0, mid = 0;
@@ -297,6 +303,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->csr_ready) cudaEventDestroy(s->csr_ready);
+    for (cudaEvent_t e : s->slab_ev) cudaEventDestroy(e);
     delete s;
 }
 
@@ -337,16 +344,47 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         return 1;
     s->own_Y = true;
     if (s->sparse_storage) {
-        if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1) || h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) ||
-            h2d_new(s, &s->val, Y->val, s->nnz))
-            return 1;
-        if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->col_idx, s->nnz) || dev_alloc(&s->val_t, s->nnz)) return 1;
         const bool have_host_csr = Y->row_ptr && (s->nnz == 0 || (Y->col_idx && Y->val_t));
-        if (!have_host_csr || !getenv("TRMF_B200_HOST_CSR")) {
-            // by-time CSR derived in HBM from the by-series CSC just uploaded (ingest.cuh): halves the PCIe traffic
-            CUDA_TRY(csr_from_csc_device<V>(s->stream, s->num_sms, s->T, s->n, s->nnz, s->col_ptr, s->row_idx, s->val, s->row_ptr,
-                                            s->col_idx, s->val_t));
-            s->launches += 5;
+        const bool device_csr = !have_host_csr || !getenv("TRMF_B200_HOST_CSR");
+        const bool slabs = device_csr && s->nnz >= (1u << 22) && s->n >= 16 && !getenv("TRMF_B200_NO_SLAB_UPLOAD");
+        if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1)) return 1;
+        if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->col_idx, s->nnz) || dev_alloc(&s->val_t, s->nnz)) return 1;
+        if (!slabs) {
+            if (h2d_new(s, &s->row_idx, Y->row_idx, s->nnz) || h2d_new(s, &s->val, Y->val, s->nnz)) return 1;
+        } else {
+            // CSC in ~8 nnz-balanced series slabs on the copy stream: the F-update of slab b overlaps the upload of b+1...
+            if (dev_alloc(&s->row_idx, s->nnz) || dev_alloc(&s->val, s->nnz)) return 1;
+            CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&s->csr_ready, cudaEventDisableTiming));
+            CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));                 // allocations + factor uploads are ordered on s->stream
+            CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
+            const int nslab = 8;
+            s->slab_j.assign(1, 0);
+            for (int b = 1; b < nslab; ++b) {
+                const uint64_t target = s->nnz / nslab * b;
+                const uint64_t *lo = std::lower_bound(Y->col_ptr, Y->col_ptr + s->n + 1, target);
+                size_t j = (size_t)(lo - Y->col_ptr);
+                if (j > s->n) j = s->n;
+                if (j > s->slab_j.back()) s->slab_j.push_back(j);
+            }
+            if (s->slab_j.back() < s->n) s->slab_j.push_back(s->n);
+            for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
+                const uint64_t e0 = Y->col_ptr[s->slab_j[b]], e1 = Y->col_ptr[s->slab_j[b + 1]];
+                if (e1 > e0) {
+                    CUDA_TRY(cudaMemcpyAsync(s->row_idx + e0, Y->row_idx + e0, (e1 - e0) * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                    CUDA_TRY(cudaMemcpyAsync(s->val + e0, (const V *)Y->val + e0, (e1 - e0) * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
+                }
+                cudaEvent_t ev;
+                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                CUDA_TRY(cudaEventRecord(ev, s->copy_stream));
+                s->slab_ev.push_back(ev);
+            }
+            s->slabs_pending = true;
+        }
+        if (device_csr) {
+            // by-time CSR derived in HBM from the by-series CSC (ingest.cuh): halves the PCIe traffic.  Issued by the
+            // first consumer (need_csr) so that the F-update is not queued behind it.
+            s->csr_deferred = true;
         } else {
             // caller's CSR arrays as given: copy on the side stream, publish with an event
             CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
@@ -457,6 +495,7 @@ extern "C" int trmf_b200_set_stream(S *s, void *cuda_stream) {
     CUDA_TRY(cudaSetDevice(s->device));
     if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     s->csr_pending = false;
+    s->slabs_pending = false;   // (everything has landed; a deferred CSR build simply runs on the new stream)
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     s->stream = (cudaStream_t)cuda_stream;
@@ -470,8 +509,24 @@ extern "C" int trmf_b200_sync(S *s) {
     return 0;
 }
 
-// make the session stream wait for the side-stream upload of the by-time CSR (first consumer calls this)
+// the whole by-series CSC has landed (a consumer other than the slab-wise F-update calls this)
+static int wait_slabs(S *s) {
+    if (!s->slabs_pending) return 0;
+    for (cudaEvent_t e : s->slab_ev) CUDA_TRY(cudaStreamWaitEvent(s->stream, e, 0));
+    s->slabs_pending = false;
+    return 0;
+}
+
+// by-time CSR ready on the session stream (first consumer calls this): either wait for the side-stream upload of
+// the caller's arrays, or build it now from the by-series CSC (ingest.cuh)
 static int need_csr(S *s) {
+    if (s->csr_deferred) {
+        if (wait_slabs(s)) return 1;
+        CUDA_TRY(csr_from_csc_device<V>(s->stream, s->num_sms, s->T, s->n, s->nnz, s->col_ptr, s->row_idx, s->val, s->row_ptr,
+                                        s->col_idx, s->val_t));
+        s->launches += 5;
+        s->csr_deferred = false;
+    }
     if (!s->csr_pending) return 0;
     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
     s->csr_pending = false;
@@ -710,10 +765,22 @@ extern "C" int trmf_b200_f_update(S *s) {
     if (s->missing) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev2, s->stream));
         const int fk = f_kernel_choice(k, s->W);
+        if (fk != F_KERNEL_MMA && wait_slabs(s)) return 1;
         if (fk == F_KERNEL_MMA) {
             if (mma_scratch(s)) return 1;
-            if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs, s->H,
-                                          (V *)nullptr, k, s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
+            if (s->slabs_pending) {
+                // first F-update of a host-buffer session: one launch per series slab, each as soon as its slab has landed
+                for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
+                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
+                    const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
+                    if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, s->val, s->W, s->T, s->Xs,
+                                                            s->invs, s->H + j0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(j1 - j0),
+                                                            s->queue, &s->launches, nullptr, 0, nullptr, b == 0))
+                        return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                }
+                s->slabs_pending = false;
+            } else if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+                                                           s->H, (V *)nullptr, k, s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
                 return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (fk == F_KERNEL_FFMA) {
             if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
@@ -737,6 +804,7 @@ extern "C" int trmf_b200_f_update(S *s) {
         if (s->timing) CUDA_TRY(cudaEventRecord(s->ev3, s->stream));
     } else {
         // dense mode: YtW = Y^T W, G = W^T W + lI I, one factorisation, n solves (trmf.cpp:319-337)
+        if (wait_slabs(s)) return 1;
         if (s->sparse_storage) {
             if (sparse_pass<MODE_SPMM>(s, s->col_ptr, s->row_idx, s->val, s->W, nullptr, s->tmp_nk, s->n, -1)) return 1;
             // widen to fp64 for the solve
@@ -854,13 +922,26 @@ extern "C" int trmf_b200_x_update(S *s) {
         // trial point and the acceptance test (rf_tron.h:183-236)
         LAUNCH(s, tron_trial_kernel, eg, 256, 0, s->W, s->s, s->g, s->r, s->wnew, tk, s->part, s->ticket,
                s->scal + SC_GS, s->scal + SC_SR);
-        if (dot(s, s->s, s->s, tk, SC_DHD)) return 1;   // |s|^2, only feeds the (inert) trust radius / verbose line
+        if (dot(s, s->s, s->s, tk, SC_SS)) return 1;   // |s|^2, only feeds the (inert) trust radius / verbose line
+        // fun(w + s), rf_tron.h:191.  The objective is exactly quadratic in W for fixed H, so with the per-time-stamp
+        // Grams in hand f(w+s) = f(w) + g's + 0.5 s'Hs costs one more Gram-based Hessian-vector product (0.08 ms at C2)
+        // instead of a third walk over Omega (1.5 ms), and its rounding error scales with the reduction itself, not
+        // with f (two independent evaluations cancel ~7 digits).  TRMF_B200_WALK_FNEW evaluates it by the walk.
+        const bool quad_fnew = s->missing && s->gram_now && !getenv("TRMF_B200_WALK_FNEW");
+        if (quad_fnew) {
+            if (gram_hv_launch(s, s->s, s->Hd, true)) return 1;   // scal[SC_DHD] = s'Hs
+        }
         if (read_scalars(s)) return 1;
-        const double gs = s->h_scal[SC_GS], sr = s->h_scal[SC_SR], snorm = std::sqrt(s->h_scal[SC_DHD]);
+        const double gs = s->h_scal[SC_GS], sr = s->h_scal[SC_SR], snorm = std::sqrt(s->h_scal[SC_SS]);
         const double prered = -0.5 * (gs - sr);
-        if (fun_launch(s, s->wnew)) return 1;
-        if (read_scalars(s)) return 1;
-        const double fnew = fun_combine(s);
+        double fnew;
+        if (quad_fnew) {
+            fnew = f + gs + 0.5 * s->h_scal[SC_DHD];
+        } else {
+            if (fun_launch(s, s->wnew)) return 1;
+            if (read_scalars(s)) return 1;
+            fnew = fun_combine(s);
+        }
         const double actred = f - fnew;
         // trust-radius bookkeeping (rf_tron.h:196-217); inert under pure_cg but printed at verbose >= 2
         delta = std::min(delta, snorm);

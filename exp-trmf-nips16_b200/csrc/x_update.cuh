@@ -178,7 +178,7 @@ static inline size_t sparse_pass_smem(int k, int warps) {
 // device memory (double), reductions deterministic.
 // ---------------------------------------------------------------------------
 enum {   // slots of the device scalar block
-    SC_F = 0, SC_FBASE, SC_FLOSS, SC_FNEW, SC_GG, SC_RTR, SC_DHD, SC_RNEW, SC_GS, SC_SR, SC_TMP, SC_TMP2,
+    SC_F = 0, SC_FBASE, SC_FLOSS, SC_FNEW, SC_GG, SC_RTR, SC_DHD, SC_RNEW, SC_GS, SC_SR, SC_TMP, SC_TMP2, SC_SS,
     SC_COUNT = 16
 };
 
