@@ -343,7 +343,8 @@ def run_b200_arm(args, cfg, rank, world, local_rank):
                 "entries_per_s": nnz_loc / (fk * 1e-3)}
 
     # ---- end to end through the public host-buffer API ----
-    e2e = run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0, n_loc, nnz_loc, nnz_total)
+    e2e = None if args.no_e2e else run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0,
+                                           n_loc, nnz_loc, nnz_total)
 
     s.close()
     lib.trmf_b200_free_synth(ctypes.byref(sd))
@@ -439,6 +440,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (large configs: it pins every slab on the host)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))

@@ -848,10 +848,12 @@ extern "C" int trmf_b200_x_update(S *s) {
     int cur = SC_RTR, nxt = SC_RNEW;
     if (s->missing) {
         if (gram_prepare(s)) return 1;
-        // Building the Grams costs about three walks over Omega (measured at C2: 6.3 ms vs 2.1 ms per Hv walk), so
-        // it pays off from ~4 CG steps on; the previous X-update's step count is the predictor (ALS needs fewer and
-        // fewer CG steps as it converges).  TRMF_B200_FORCE_GRAM_HV pins the choice for tests.
-        s->gram_now = s->gram_state == 1 && (s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
+        // With the mma kernel the Gram build also delivers fun(w), grad(w) and (through the quadratic identity) fun(w+s):
+        // 3.4 ms at C2 against 2.3 + 1.5 ms for the two walks it replaces, before a single CG step is counted -- always
+        // taken.  The FFMA Gram kernel only replaces the Hv walks (6.3 ms vs 2.1 ms each): worth it from ~4 CG steps
+        // on, the previous X-update's step count being the predictor.  TRMF_B200_FORCE_GRAM_HV pins the choice for tests.
+        const bool fusable = f_kernel_choice(s->k, s->H) == F_KERNEL_MMA && !getenv("TRMF_B200_NO_FUSED_GRAD");
+        s->gram_now = s->gram_state == 1 && (fusable || s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
         bool fused = false;   // fun(w), grad(w) came out of the Gram build's own gather
         if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
             int rc;
