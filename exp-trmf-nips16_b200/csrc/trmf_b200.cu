@@ -345,6 +345,20 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     s->own_Y = true;
     if (s->sparse_storage) {
         const bool have_host_csr = Y->row_ptr && (s->nnz == 0 || (Y->col_idx && Y->val_t));
+        const bool have_host_csc = Y->col_ptr && (s->nnz == 0 || (Y->row_idx && Y->val));
+        if (!have_host_csc && !have_host_csr) return fail("sparse Y carries neither a complete CSR nor a complete CSC half");
+        if (!have_host_csc) {
+            // CSR-only PyMatrix (trmf.rf_util.PyMatrix(..., twin=False) of a csr_matrix): upload it and derive the
+            // by-series CSC on the device -- the same stable transpose with the roles of rows and columns swapped
+            if (h2d_new(s, &s->row_ptr, Y->row_ptr, s->T + 1) || h2d_new(s, &s->col_idx, Y->col_idx, s->nnz) ||
+                h2d_new(s, &s->val_t, Y->val_t, s->nnz))
+                return 1;
+            if (dev_alloc(&s->col_ptr, s->n + 1) || dev_alloc(&s->row_idx, s->nnz) || dev_alloc(&s->val, s->nnz)) return 1;
+            CUDA_TRY(csr_from_csc_device<V>(s->stream, s->num_sms, s->n, s->T, s->nnz, s->row_ptr, s->col_idx, s->val_t, s->col_ptr,
+                                            s->row_idx, s->val));
+            s->launches += 5;
+            return 0;
+        }
         const bool device_csr = !have_host_csr || !getenv("TRMF_B200_HOST_CSR");
         const bool slabs = device_csr && s->nnz >= (1u << 22) && s->n >= 16 && !getenv("TRMF_B200_NO_SLAB_UPLOAD");
         if (h2d_new(s, &s->col_ptr, Y->col_ptr, s->n + 1)) return 1;

@@ -71,11 +71,19 @@ class PyMatrix(ctypes.Structure):
         ("type", ctypes.c_int32),
     ]
 
-    def __init__(self, A, dtype=np.float32, major=None):
+    def __init__(self, A, dtype=np.float32, major=None, twin=True):
         """``major`` ('row' / 'col', optional, additive to the reference signature)
         settles the type tag of arrays that are both C- and F-contiguous (a
         single row or column, e.g. W with k == 1), which the reference would tag
-        COLMAJOR and then reject for W/H."""
+        COLMAJOR and then reject for W/H.
+
+        ``twin`` (additive): the reference always builds BOTH sparse orientations
+        on the host (two scipy conversions, rf_util.py:88-98).  ``twin=False``
+        keeps only the orientation ``A`` already has (CSC for a csc_matrix, CSR
+        otherwise) and leaves the other three pointers NULL: the CUDA library
+        derives the missing half on the device, bit-identically
+        (``csrc/ingest.cuh``).  ``trmf.train`` uses this; such a PyMatrix is not
+        valid input for the reference's own core."""
         super().__init__()
         if A is None:
             return
@@ -88,20 +96,25 @@ class PyMatrix(ctypes.Structure):
                 # explicit COO keeps duplicates apart in the reference (rf_util.py:100-119);
                 # here they are summed, which is what every caller in trmf.py relies on.
                 A = A.tocsr()
-            csr = sps.csr_matrix(A)
-            csc = sps.csc_matrix(A)
-            if not csr.has_sorted_indices:
-                csr = csr.sorted_indices()
-            if not csc.has_sorted_indices:
-                csc = csc.sorted_indices()
             self.type = PyMatrix.SPARSE
-            self.nnz = int(csr.indptr[-1])
-            buf["row_ptr"] = csr.indptr.astype(np.uint64)
-            buf["col_idx"] = csr.indices.astype(np.uint32)
-            buf["val_t"] = csr.data.astype(dtype)
-            buf["col_ptr"] = csc.indptr.astype(np.uint64)
-            buf["row_idx"] = csc.indices.astype(np.uint32)
-            buf["val"] = csc.data.astype(dtype)
+            want_csr = twin or A.format != "csc"
+            want_csc = twin or A.format == "csc"
+            if want_csr:
+                csr = sps.csr_matrix(A)
+                if not csr.has_sorted_indices:
+                    csr = csr.sorted_indices()
+                self.nnz = int(csr.indptr[-1])
+                buf["row_ptr"] = csr.indptr.astype(np.uint64)
+                buf["col_idx"] = csr.indices.astype(np.uint32)
+                buf["val_t"] = csr.data.astype(dtype, copy=False)
+            if want_csc:
+                csc = sps.csc_matrix(A)
+                if not csc.has_sorted_indices:
+                    csc = csc.sorted_indices()
+                self.nnz = int(csc.indptr[-1])
+                buf["col_ptr"] = csc.indptr.astype(np.uint64)
+                buf["row_idx"] = csc.indices.astype(np.uint32)
+                buf["val"] = csc.data.astype(dtype, copy=False)
         elif isinstance(A, np.ndarray):
             arr = A.astype(dtype)   # order='K': keeps the caller's memory layout
             if not (arr.flags.c_contiguous or arr.flags.f_contiguous):

@@ -266,7 +266,9 @@ def train(Y, model, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1,
     (reference trmf.py:253-264).  ``threads`` is accepted for compatibility."""
     if model.transform is not None:
         Y = model.transform.preprocess(Y)
-    _clib.train(PyMatrix(Y, dtype=model.W.dtype), model.lag_set,
+    # one sparse orientation only: the library derives the other on the device (the reference's PyMatrix spends
+    # seconds in scipy building both at the sizes of BASELINE config 2, rf_util.py:88-98)
+    _clib.train(PyMatrix(Y, dtype=model.W.dtype, twin=False), model.lag_set,
                 model.pyW, model.pyH, model.pylag_val, warm_start=True,
                 lambdaI=lambdaI, lambdaAR=lambdaAR, lambdaLag=lambdaLag,
                 max_iter=max_iter, period_W=period_W, period_H=period_H, period_Lag=period_Lag,

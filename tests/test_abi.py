@@ -141,3 +141,21 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_pymatrix_single_orientation_leaves_the_other_half_null():
+    """twin=False (what trmf.train passes down): only the orientation the caller's matrix already has is
+    marshalled; the library derives the other one on the device."""
+    import scipy.sparse as sps
+    from trmf.rf_util import PyMatrix
+    A = sps.random(30, 20, density=0.3, format="csr", random_state=np.random.RandomState(0), dtype=np.float64)
+    csr = PyMatrix(A, np.float32, twin=False)
+    assert csr.type == PyMatrix.SPARSE and csr.nnz == A.nnz and csr.row_ptr and csr.col_idx and csr.val_t
+    assert not csr.col_ptr and not csr.row_idx and not csr.val
+    csc = PyMatrix(A.tocsc(), np.float32, twin=False)
+    assert csc.nnz == A.nnz and csc.col_ptr and csc.row_idx and csc.val
+    assert not csc.row_ptr and not csc.col_idx and not csc.val_t
+    both = PyMatrix(A, np.float32)
+    assert both.row_ptr and both.col_ptr
+    assert np.array_equal(both.py_buf["row_ptr"], csr.py_buf["row_ptr"]) and np.array_equal(both.py_buf["col_idx"], csr.py_buf["col_idx"])
+    assert np.array_equal(both.py_buf["col_ptr"], csc.py_buf["col_ptr"]) and np.array_equal(both.py_buf["row_idx"], csc.py_buf["row_idx"])

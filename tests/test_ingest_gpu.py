@@ -49,21 +49,53 @@ def test_csc_only_pymatrix_trains_like_twin_storage(dtype, monkeypatch):
     Y = p["Ysp"].astype(dtype)
     W0, H0, L0 = (a.astype(dtype) for a in (p["W0"], p["H0"], p["L0"]))
     outs = []
-    for mode in ("device", "host", "csc_only"):
+    for mode in ("device", "host", "csc_only", "csr_only", "no_slabs"):
         if mode == "host":
             monkeypatch.setenv("TRMF_B200_HOST_CSR", "1")
         else:
             monkeypatch.delenv("TRMF_B200_HOST_CSR", raising=False)
-        pm = PyMatrix(Y, dtype)
+        if mode == "no_slabs":
+            monkeypatch.setenv("TRMF_B200_NO_SLAB_UPLOAD", "1")
         if mode == "csc_only":
-            pm.row_ptr = None
-            pm.col_idx = None
-            pm.val_t = None
+            pm = PyMatrix(Y.tocsc(), dtype, twin=False)
+            assert not pm.row_ptr and not pm.col_idx and not pm.val_t and pm.col_ptr
+        elif mode == "csr_only":
+            pm = PyMatrix(Y.tocsr(), dtype, twin=False)
+            assert not pm.col_ptr and not pm.row_idx and not pm.val and pm.row_ptr
+        else:
+            pm = PyMatrix(Y, dtype)
         s = Session(pm, p["lags"], W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
         s.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
         outs.append(s.download())
         s.close()
-    for a, b in zip(outs[0], outs[1]):
-        assert np.array_equal(a, b)      # same arrays in HBM either way -> bitwise the same factors
-    for a, b in zip(outs[0], outs[2]):
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)      # same arrays in HBM either way -> bitwise the same factors
+
+
+def test_slab_upload_trains_like_a_single_copy(monkeypatch):
+    """Above 4M entries a host-buffer session uploads the CSC in nnz-balanced series slabs on a copy stream and
+    the first F-update runs slab by slab; the factors must not depend on that."""
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    dtype = np.float32
+    rng = np.random.RandomState(3)
+    T, n, k = 3000, 2500, 40
+    mask = rng.rand(T, n) < 0.62
+    mask[:, 7] = False
+    Y = sps.csr_matrix(np.where(mask, rng.randn(T, n) + 3.0, 0.0).astype(dtype))
+    assert Y.nnz >= (1 << 22)
+    lags = np.array([1, 7, 24], dtype=np.uint32)
+    W0, H0, L0 = rng.rand(T, k).astype(dtype), rng.rand(n, k).astype(dtype), rng.randn(3, k).astype(dtype)
+    outs = []
+    for slabs in (True, False):
+        if slabs:
+            monkeypatch.delenv("TRMF_B200_NO_SLAB_UPLOAD", raising=False)
+        else:
+            monkeypatch.setenv("TRMF_B200_NO_SLAB_UPLOAD", "1")
+        s = Session(PyMatrix(Y, dtype), lags, W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+        s.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
+        outs.append(s.download())
+        s.close()
+    for a, b in zip(*outs):
         assert np.array_equal(a, b)

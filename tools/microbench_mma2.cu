@@ -37,7 +37,12 @@ __device__ __forceinline__ void mma_f16a(float (&d)[4], const uint32_t (&a)[4], 
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// KIND 0: tf32 k8, 1: f16 k16.  XF independent FFMAs per HMMA.
+__device__ __forceinline__ void mma_f16_k8(float (&d)[4], const uint32_t a0, const uint32_t a1, const uint32_t b0) {
+    asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a0), "r"(a1), "r"(b0));
+}
+// KIND 0: tf32 k8, 1: f16 k16, 2: f16 k8.  XF independent FFMAs per HMMA.
 template <int KIND, int XF>
 __global__ void k_mix(float *out, int iters, long long *cyc) {
     float acc[9][4], f[8];
@@ -54,7 +59,9 @@ __global__ void k_mix(float *out, int iters, long long *cyc) {
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            if (KIND == 0) mma_tf32(acc[i], a0, a1, a2, a3, b0, b1); else mma_f16(acc[i], a0, a1, a2, a3, b0, b1);
+            if (KIND == 0) mma_tf32(acc[i], a0, a1, a2, a3, b0, b1);
+            else if (KIND == 1) mma_f16(acc[i], a0, a1, a2, a3, b0, b1);
+            else mma_f16_k8(acc[i], a0, a1, b0);
 #pragma unroll
             for (int x = 0; x < XF; ++x) f[(i * XF + x) & 7] = fmaf(f[(i * XF + x) & 7], m, c);
         }
@@ -167,10 +174,11 @@ int main() {
     do {                                                                                                  \
         k_mix<KIND, XF><<<sms, warps * 32>>>(out, it, cyc);                                               \
         double c = maxcyc(sms);                                                                           \
-        printf("%s + %d FFMA per HMMA, 16 warps/SM: %.2f clk per HMMA per SMSP\n", KIND ? "HMMA.16816.F16" : "HMMA.1688.TF32", XF, \
+        printf("%s + %d FFMA per HMMA, 16 warps/SM: %.2f clk per HMMA per SMSP\n", KIND == 2 ? "HMMA.1688.F16" : KIND ? "HMMA.16816.F16" : "HMMA.1688.TF32", XF, \
                c / (4.0 * 9 * it));                                                                       \
     } while (0)
     MIX(0, 0); MIX(0, 2); MIX(0, 4); MIX(0, 6); MIX(0, 8); MIX(0, 12);
+    MIX(2, 0); MIX(2, 2); MIX(2, 4);
     MIX(1, 0); MIX(1, 2); MIX(1, 4); MIX(1, 6); MIX(1, 8); MIX(1, 12);
     // fp16-split Gram
     std::vector<float> hX(EV * RS);
