@@ -156,8 +156,12 @@ __global__ void colscale_apply_kernel(const float *__restrict__ X, size_t rows, 
 //              and ::grad, trmf.cpp:231-267): per entry z = <Wv_j, x_e> - Y_je (fp32 dot), F[j] (+)= sum_e z x_e
 //              (fp32 FMAs, fp64 every 128 entries) and frow[j] = sum_e z^2 (fp64) -- the X-update then needs no
 //              separate walk over Omega for fun(w) / grad(w).
+// MODE_DEFER : MODE_SOLVE without the solve: the assembled fp64 system (lower triangle + rhs row, (K+1) x (K+1)) goes
+//              to sys[j] and chol_solve_kernel factors it afterwards.  A CTA that solves in place keeps its 4 warps
+//              off the tensor pipe for the length of a 128-thread Cholesky; with few entries per series (C5: 2 000
+//              at k = 64) that is half of the F-update, while the separate kernel runs 6-16 solves per SM at once.
 // X is the column-scaled factor (colscale_apply_kernel), invs its inverse scales.
-enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3 };
 template <int K, int NW, int MINB, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
@@ -165,7 +169,7 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                     float *__restrict__ Gout, double lambda, uint32_t nseries, unsigned *__restrict__ queue,
                     const float *__restrict__ Wv, int gaccum, double *__restrict__ frow) {
     typedef Cfg<K> C;
-    constexpr bool SOLVE = MODE == MODE_SOLVE, GRAD = MODE == MODE_GRAD;
+    constexpr bool SOLVE = MODE == MODE_SOLVE || MODE == MODE_DEFER, GRAD = MODE == MODE_GRAD, DEFER = MODE == MODE_DEFER;
     constexpr int NC = C::NC, MT = C::MT, NT = C::NT, CH = C::CH, RS = C::RS, STAGES = C::STAGES, NQ = C::NQ;
     constexpr int SF = C::STAGE_FLOATS, ld = C::ld, NTH = NW * 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -391,7 +395,10 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
                 A[K * ld + c] = s * (double)invs[c];
             }
             __syncthreads();
-            if (SOLVE) {
+            if (DEFER) {   // frow carries the scratch: one (K+1) x ld fp64 system per series
+                double *dst = frow + (size_t)j * ((K + 1) * ld);
+                for (int p = tid; p < (K + 1) * ld; p += NTH) dst[p] = A[p];
+            } else if (SOLVE) {
                 if (tid < K) A[tid * ld + tid] += lambda;      // trmf.cpp:393
                 block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, K);   // starts and ends with __syncthreads
                 if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
@@ -431,6 +438,29 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
     }
 }
 
+// The solve of MODE_DEFER: one CTA per system at a time, many CTAs per SM.  Same arithmetic as the in-kernel solve
+// (block_chol_solve_blocked does not depend on the block size), so the factors are bit-identical either way.
+template <int K>
+__global__ void __launch_bounds__(128)
+chol_solve_kernel(const uint64_t *__restrict__ ptr, const double *__restrict__ sys, float *__restrict__ F, double lambda,
+                  uint32_t nseries) {
+    constexpr int ld = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A = reinterpret_cast<double *>(smem_raw);
+    double *dinv = A + (size_t)(K + 1) * ld;
+    const int tid = threadIdx.x;
+    for (uint32_t j = blockIdx.x; j < nseries; j += gridDim.x) {
+        if (ptr[j + 1] == ptr[j]) continue;             // no observation: the row keeps its value (trmf.cpp:374)
+        const double *src = sys + (size_t)j * ((K + 1) * ld);
+        for (int p = tid; p < (K + 1) * ld; p += 128) A[p] = src[p];
+        __syncthreads();
+        if (tid < K) A[tid * ld + tid] += lambda;       // trmf.cpp:393
+        block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, K);   // starts and ends with __syncthreads
+        if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
+        __syncthreads();
+    }
+}
+
 // out = scale * sum_i v[i], deterministic two-level fp64 sum (MODE_GRAD's per-row losses -> the objective's loss part)
 __global__ void sum_rows_kernel(const double *__restrict__ v, size_t n, double scale, double *part, unsigned *ticket, double *out) {
     __shared__ double red[32];
@@ -441,6 +471,32 @@ __global__ void sum_rows_kernel(const double *__restrict__ v, size_t n, double s
 }
 
 }   // namespace fm
+
+static inline size_t f_update_mma_sys_doubles(int k) { return (size_t)(k + 1) * (k + 1); }
+
+// solve the nseries systems a MODE_DEFER launch left in `sys`
+static inline int f_update_mma_solve(cudaStream_t st, int num_sms, const uint64_t *ptr, const double *sys, V *F, int k, double lambda,
+                                     uint32_t nseries, unsigned long long *launches) {
+#define FS_CASE(KK)                                                                                             \
+    case KK: {                                                                                                  \
+        const size_t smem = sizeof(double) * ((size_t)(KK + 1) * (KK + 1) + KK);                                \
+        auto kfn = fm::chol_solve_kernel<KK>;                                                                   \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+        int per_sm = 0;                                                                                         \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem) != cudaSuccess) return 1;    \
+        unsigned grid = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)num_sms;                                \
+        if (grid > nseries) grid = nseries;                                                                     \
+        kfn<<<grid ? grid : 1, 128, smem, st>>>(ptr, sys, F, lambda, nseries);                                  \
+        break;                                                                                                  \
+    }
+    switch (k) {
+        FS_CASE(8) FS_CASE(16) FS_CASE(20) FS_CASE(24) FS_CASE(32) FS_CASE(40) FS_CASE(48) FS_CASE(56) FS_CASE(60) FS_CASE(64)
+        default: return 1;
+    }
+#undef FS_CASE
+    ++*launches;
+    return cudaGetLastError() != cudaSuccess;
+}
 
 static inline bool f_update_mma_supported(int k) {
     switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: case 56: case 60: case 64: return true; }
@@ -507,8 +563,10 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
 #else   // float64 build: the generic kernel (fp64 FMAs) is the parity path
 
 static inline bool f_update_mma_supported(int) { return false; }
+static inline size_t f_update_mma_sys_doubles(int) { return 0; }
+static inline int f_update_mma_solve(cudaStream_t, int, const uint64_t *, const double *, V *, int, double, uint32_t, unsigned long long *) { return 1; }
 namespace fm {
-enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2 };
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3 };
 __global__ void sum_rows_kernel(const double *, size_t, double, double *, unsigned *, double *) {}
 }
 template <int MODE>

@@ -123,6 +123,8 @@ struct trmf_b200_session {
     V *Xs = nullptr;                  // column-scaled copy of the factor the mma Gram kernel reads (max(T, n) x k)
     float *invs = nullptr;            // its k inverse scales
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
+    double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
+    size_t sys_batch = 0;             // series per batch
     int gram_state = 0;               // 0 = not decided, 1 = enabled, -1 = disabled
     int prev_cg = -1;                 // CG steps of the previous x_update of this session (-1: none yet)
     bool gram_now = false;            // this x_update goes through the Grams
@@ -282,7 +284,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->frow);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->frow); dev_free(s->sys);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -768,6 +770,35 @@ static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd) {
     return 0;
 }
 
+// sparse F-update of the series [j0, j1) with the mma kernel.  Default: the kernel only assembles the fp64 systems
+// (MODE_DEFER) in batches of at most ~1 GB of scratch and chol_solve_kernel factors each batch; the in-kernel solve
+// (TRMF_B200_INLINE_SOLVE) gives bit-identical factors.
+static int mma_f_range(S *s, size_t j0, size_t j1, bool rescale) {
+    const int k = s->k;
+    if (getenv("TRMF_B200_INLINE_SOLVE")) {
+        if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+                                                s->H + j0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(j1 - j0), s->queue,
+                                                &s->launches, nullptr, 0, nullptr, rescale))
+            return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return 0;
+    }
+    const size_t sysd = f_update_mma_sys_doubles(k);
+    if (!s->sys) {
+        s->sys_batch = std::max<size_t>(1, std::min<size_t>(s->n, ((size_t)1 << 30) / (sysd * sizeof(double))));
+        if (dev_alloc(&s->sys, s->sys_batch * sysd)) return 1;
+    }
+    for (size_t b0 = j0; b0 < j1; b0 += s->sys_batch) {
+        const size_t b1 = std::min(j1, b0 + s->sys_batch);
+        if (f_update_mma_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+                                                s->H + b0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(b1 - b0), s->queue,
+                                                &s->launches, nullptr, 0, s->sys, rescale && b0 == j0) ||
+            f_update_mma_solve(s->stream, s->num_sms, s->col_ptr + b0, s->sys, s->H + b0 * (size_t)k, k, s->lambdaI, (uint32_t)(b1 - b0),
+                               &s->launches))
+            return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return 0;
+}
+
 // --------------------------------------------------------------------------
 // the three phases
 // --------------------------------------------------------------------------
@@ -786,16 +817,10 @@ extern "C" int trmf_b200_f_update(S *s) {
                 // first F-update of a host-buffer session: one launch per series slab, each as soon as its slab has landed
                 for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
                     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
-                    const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
-                    if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, s->val, s->W, s->T, s->Xs,
-                                                            s->invs, s->H + j0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(j1 - j0),
-                                                            s->queue, &s->launches, nullptr, 0, nullptr, b == 0))
-                        return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+                    if (mma_f_range(s, s->slab_j[b], s->slab_j[b + 1], b == 0)) return 1;
                 }
                 s->slabs_pending = false;
-            } else if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
-                                                           s->H, (V *)nullptr, k, s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))
-                return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            } else if (mma_f_range(s, 0, s->n, true)) return 1;
         } else if (fk == F_KERNEL_FFMA) {
             if (f_update_tiled_launch<true>(s->stream, s->num_sms, s->col_ptr, s->row_idx, s->val, s->W, s->H, (V *)nullptr, k,
                                             s->lambdaI, (uint32_t)s->n, s->queue, &s->launches))

@@ -215,6 +215,7 @@ def test_python_surface_end_to_end():
                                  {"TRMF_B200_FORCE_GRAM_HV": "1"}, {"TRMF_B200_F_KERNEL": "ffma"}, {"TRMF_B200_F_KERNEL": "mma"},
                                  {"TRMF_B200_NO_FUSED_GRAD": "1"}, {"TRMF_B200_F_KERNEL": "ffma", "TRMF_B200_FORCE_GRAM_HV": "1"},
                                  {"TRMF_B200_FORCE_GRAM_HV": "1", "TRMF_B200_NO_FUSED_GRAD": "1"},
+                                 {"TRMF_B200_INLINE_SOLVE": "1"}, {"TRMF_B200_WALK_FNEW": "1"},
                                  {"TRMF_B200_GENERIC_F": "1", "TRMF_B200_NO_GRAM_HV": "1", "TRMF_B200_GENERIC_PASS": "1"}])
 def test_float32_kernel_variants_agree(env, monkeypatch):
     """Every fp32 kernel variant (mma / FFMA-tiled / generic Gram kernel, Gram-based / direct Hv, gradient fused
