@@ -398,7 +398,7 @@ def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_ra
     copied = ("col_ptr", "row_idx", "val") if not os.environ.get("TRMF_B200_HOST_CSR") else tuple(pm.py_buf)
     h2d = sum(pm.py_buf[name].nbytes for name in copied) + W0.nbytes + H0.nbytes + L0.nbytes
     d2h_bytes = W0.nbytes + H0.nbytes + L0.nbytes
-    steps = max(1, min(args.steps, 5))
+    steps = max(1, min(args.steps, 9))
     times = []
     WARM = 2                      # untimed calls: the first grows the stream-ordered memory pool to its steady size
     for it in range(WARM + steps):
@@ -427,8 +427,11 @@ def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_ra
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         if it >= WARM:
             times.append(float(tt.item()))
-    sec = float(np.mean(times))
+    # median over the timed calls: the call is ~half host work (session set-up, PCIe) on a box shared with other
+    # tenants, and single calls were seen 2-5x slower than their neighbours; the mean is reported next to it
+    sec = float(np.median(times))
     return {"value": nnz_total / sec, "unit": "entries/s", "ms_per_step": 1e3 * sec, "steps": steps,
+            "ms_per_step_mean": 1e3 * float(np.mean(times)), "ms_per_step_min": 1e3 * float(np.min(times)), "statistic": "median",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes),
             "api": "c_trmf_train (host PyMatrix buffers, pinned; CSR half built on device)" if world == 1 else "trmf.session.Session(host slab) + NCCL"}
 

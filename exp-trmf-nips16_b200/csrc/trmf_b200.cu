@@ -210,12 +210,22 @@ static void pinned_put(double *p) {
 // --------------------------------------------------------------------------
 static int session_common_init(S *s) {
     CUDA_TRY(cudaSetDevice(s->device));
-    cudaDeviceProp prop;
-    CUDA_TRY(cudaGetDeviceProperties(&prop, s->device));
-    s->num_sms = prop.multiProcessorCount;
-    if (prop.major < 10)
-        return fail("device %d (%s, sm_%d%d) is not a Blackwell (sm_100a) GPU; this library has no other code path",
-                    s->device, prop.name, prop.major, prop.minor);
+    {   // (cudaGetDeviceProperties costs milliseconds: two attribute queries, cached per device)
+        static int sms_cache[64] = {0}, major_cache[64] = {0};
+        const int d = s->device;
+        if (d < 0 || d >= 64) return fail("device index %d out of range", d);
+        if (sms_cache[d] == 0) {
+            int sms = 0, major = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, d));
+            CUDA_TRY(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d));
+            major_cache[d] = major;
+            sms_cache[d] = sms;
+        }
+        s->num_sms = sms_cache[d];
+        if (major_cache[d] < 10)
+            return fail("device %d (compute capability %d.x) is not a Blackwell (sm_100a) GPU; this library has no other code path",
+                        d, major_cache[d]);
+    }
     if (pool_setup(s->device)) return 1;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
@@ -750,19 +760,30 @@ static int gram_prepare(S *s) {
     return 0;
 }
 
-static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd) {
+// loss part of the Hessian-vector product from the per-time-stamp Grams: out (+)= G_i v_i for every time stamp
+static int gram_matvec(S *s, const V *v, V *out, bool accum, double *dhd) {
     const int k = s->k;
     const int WARPS = 8;
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((s->T + WARPS - 1) / WARPS, (size_t)s->num_sms * 8));
-    const size_t tk = s->T * (size_t)k;
+#ifdef TRMF_F32
+    if (!getenv("TRMF_B200_GENERIC_GRAM_MATVEC")) {
+#define GM_CASE(KK) case KK: LAUNCH(s, (gram_matvec4_kernel<KK, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, s->T, accum, s->part, s->ticket, dhd); return 0;
+        switch (k) { GM_CASE(8) GM_CASE(16) GM_CASE(20) GM_CASE(24) GM_CASE(32) GM_CASE(40) GM_CASE(48) default: break; }   // (k >= 56: the generic row loop)
+#undef GM_CASE
+    }
+#endif
+    if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd);
+    else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd);
+    return 0;
+}
+
+static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd) {
+    const size_t tk = s->T * (size_t)s->k;
     if (base_apply(s, d, Hd)) return 1;
     if (s->world == 1) {
-        double *dhd = want_dhd ? s->scal + SC_DHD : nullptr;
-        if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, d, Hd, k, s->T, true, s->part, s->ticket, dhd);
-        else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, d, Hd, k, s->T, true, s->part, s->ticket, dhd);
+        if (gram_matvec(s, d, Hd, true, want_dhd ? s->scal + SC_DHD : nullptr)) return 1;
     } else {
-        if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, d, s->part_tk, k, s->T, false, s->part, s->ticket, (double *)nullptr);
-        else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, d, s->part_tk, k, s->T, false, s->part, s->ticket, (double *)nullptr);
+        if (gram_matvec(s, d, s->part_tk, false, nullptr)) return 1;
         if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
         LAUNCH(s, axpbypcz_kernel, ew_grid(s, tk), 256, 0, 1.0, Hd, 1.0, s->part_tk, 0.0, (const V *)nullptr, Hd, tk);
         if (want_dhd && dot(s, d, Hd, tk, SC_DHD)) return 1;

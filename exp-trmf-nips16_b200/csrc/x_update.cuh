@@ -282,6 +282,60 @@ __global__ void tron_trial_kernel(const V *__restrict__ w, const V *__restrict__
 // coalesced row segment; fp64 accumulation.  out_i = (accum ? out_i : 0) + G_i s_i, and the CG
 // scalar d^T(Hd) is reduced in the same pass (deterministic two-level sum) when dhd != nullptr.
 // ---------------------------------------------------------------------------
+#ifdef TRMF_F32
+// Bandwidth-shaped variant for the fp32 build (k % 4 == 0): a warp pulls a whole k x k Gram with ceil(k*k/128)
+// independent 16-byte loads per lane (the loop over rows below issues 2 dependent-free loads per iteration and sits at
+// ~1.2 TB/s), forms the fp64 partial dot of every float4 with the matching piece of s_i, and lane t folds the k/4
+// partials of row t (the Gram is stored as a bitwise-symmetric square, so row sums = column sums).
+template <int K, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32)
+gram_matvec4_kernel(const float *__restrict__ Gm, const float *__restrict__ S, float *__restrict__ out, size_t T, bool accum,
+                    double *part, unsigned *ticket, double *dhd) {
+    constexpr int NV = K * K / 4, NIT = (NV + 31) / 32, CPR = K / 4;
+    __shared__ double red[32];
+    __shared__ __align__(16) float sS[WARPS][K];
+    __shared__ double sP[WARPS][NIT * 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    double dsum = 0.0;
+    for (size_t i = (size_t)blockIdx.x * WARPS + wid; i < T; i += (size_t)gridDim.x * WARPS) {
+        const float4 *Gi = reinterpret_cast<const float4 *>(Gm + i * (size_t)K * K);
+        float4 g[NIT];
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int p = lane + 32 * it;
+            g[it] = p < NV ? __ldg(Gi + p) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int t = lane; t < K; t += 32) sS[wid][t] = S[i * K + t];
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < NIT; ++it) {
+            const int p = lane + 32 * it;
+            if (p < NV) {
+                const int u = p / CPR, c4 = p - u * CPR;
+                const float4 sv = *reinterpret_cast<const float4 *>(&sS[wid][4 * c4]);
+                sP[wid][p] = ((double)g[it].x * (double)sv.x + (double)g[it].y * (double)sv.y) +
+                             ((double)g[it].z * (double)sv.z + (double)g[it].w * (double)sv.w);
+            }
+        }
+        __syncwarp();
+        for (int t = lane; t < K; t += 32) {
+            double a = 0.0;
+#pragma unroll
+            for (int c = 0; c < CPR; ++c) a += sP[wid][t * CPR + c];
+            const double o = (accum ? (double)out[i * K + t] : 0.0) + a;
+            const float ov = (float)o;
+            out[i * K + t] = ov;
+            dsum += (double)sS[wid][t] * (double)ov;
+        }
+        __syncwarp();
+    }
+    if (dhd != nullptr) {
+        double v = block_sum(dsum, red);
+        grid_sum_commit(v, part, ticket, dhd, 1.0, red);
+    }
+}
+#endif
+
 template <int KR, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 gram_matvec_kernel(const V *__restrict__ Gm, const V *__restrict__ S, V *__restrict__ out, int k, size_t T, bool accum,
