@@ -31,8 +31,9 @@
 // tiles of 16; warp w takes tiles w, w + NW, ...  Each warp runs its own 2-stage cp.async (LDGSTS) pipeline
 // (16 factor rows of k floats per stage, the Y values ride along with 4-byte copies) -- no CTA barrier inside
 // a series.  Fragment loads are bank-conflict free because the staging row stride RS = 8 (mod 16) floats.
-// At the end of a series the NW fp64 partials are added in warp order (bitwise reproducible), the scaling is
-// undone, lambda goes on the diagonal and the CTA runs the blocked fp64 Cholesky of common.cuh.
+// At the end of a series the NW fp64 partials are added in warp order (bitwise reproducible) and the scaling is
+// undone; the assembled system is solved by chol_solve_kernel (MODE_DEFER, default) or in place (MODE_SOLVE) with
+// the blocked fp64 Cholesky of common.cuh, or stored as the X-update's Gram (MODE_STORE / MODE_GRAD).
 #pragma once
 #include "common.cuh"
 
