@@ -80,7 +80,7 @@ extern "C" int trmf_b200_dist_init(S *s, int32_t rank, int32_t world, const void
     NCCL_TRY(g_nccl.CommInitRank(&comm, world, id, rank));
     s->nccl_comm = (void *)comm;
     s->own_comm = true;
-    if (dev_alloc(&s->part_tk, s->T * (size_t)s->k)) return 1;
+    if (dev_alloc(&s->part_tk, Tcap(s) * (size_t)s->k)) return 1;
     return 0;
 }
 
@@ -92,7 +92,7 @@ extern "C" int trmf_b200_dist_attach(S *s, S *owner) {
     s->world = owner->world;
     s->nccl_comm = owner->nccl_comm;
     s->own_comm = false;
-    if (s->world > 1 && !s->part_tk && dev_alloc(&s->part_tk, s->T * (size_t)s->k)) return 1;
+    if (s->world > 1 && !s->part_tk && dev_alloc(&s->part_tk, Tcap(s) * (size_t)s->k)) return 1;
     return 0;
 }
 

@@ -87,6 +87,21 @@ struct trmf_b200_session {
     V *Yd = nullptr;
     bool own_Y = false;
 
+    // rolling-window sessions (rolling.cuh): the whole time axis of Y stays in HBM, the solver sees the prefix
+    // [0, T) of it.  R_* = the resident full-length arrays; the by-time CSR's row_ptr / col_idx serve every
+    // window as they are (a prefix of a CSR is the CSR of the prefix), the by-series CSC is re-compacted per window.
+    bool rolling = false;
+    size_t T_cap = 0;                 // time stamps the buffers are sized for (>= every window's T)
+    size_t R_nnz = 0;                 // observed entries of the resident matrix
+    uint64_t *R_col_ptr = nullptr;
+    uint32_t *R_row_idx = nullptr;
+    V *R_val = nullptr, *R_val_t = nullptr, *R_Yd = nullptr;
+    V *win_val_t = nullptr, *win_Yd = nullptr;   // per-series affine transform applied (NormalizedTransform)
+    V *aff_a = nullptr, *aff_b = nullptr;        // its n scales / offsets
+    uint64_t *win_cnt = nullptr;                 // n + 1 per-series counts of a window
+    void *scan_tmp = nullptr;
+    size_t scan_tmp_bytes = 0;
+
     // factors
     V *W = nullptr, *H = nullptr, *th = nullptr;
     V *W_sv = nullptr, *H_sv = nullptr, *th_sv = nullptr;   // save_factors() snapshot
@@ -141,6 +156,8 @@ struct trmf_b200_session {
     double st_delta = 0, st_rnorm = 0;
 };
 typedef trmf_b200_session S;
+// time stamps to size lazily allocated T-proportional buffers for (rolling sessions grow T window by window)
+static inline size_t Tcap(const S *s) { return std::max(s->T, s->T_cap); }
 
 // multi-GPU helpers, defined in extras.cuh
 static int dist_allreduce_v(S *s, V *buf, size_t count);
@@ -208,6 +225,26 @@ static void pinned_put(double *p) {
 // --------------------------------------------------------------------------
 // creation / destruction
 // --------------------------------------------------------------------------
+// lag update: chunk the window [mid, T) so that (chunk + mid) fp64 values fit in shared memory; depends on T, so a
+// rolling session re-plans per window (same formula: a window trains exactly like a fresh session of that length)
+static int lag_plan(S *s) {
+    const size_t budget = 160 * 1024 / sizeof(double);
+    if ((size_t)s->mid + 256 > budget)
+        return fail("max lag %d too large for the lag_val kernel's shared-memory staging (limit %zu)", s->mid, budget - 256);
+    size_t chunk = std::min<size_t>(4096, budget - s->mid);
+    size_t win = s->T > (size_t)s->mid ? s->T - s->mid : 0;
+    // enough CTAs to fill the machine: k * nchunks >= 2 * SMs when the window allows
+    size_t want = std::max<size_t>(1, (2 * (size_t)s->num_sms + s->k - 1) / s->k);
+    size_t c2 = std::max<size_t>(256, (win + want - 1) / want);
+    chunk = std::min(chunk, c2);
+    s->lag_chunk = (int)chunk;
+    s->lag_nchunks = (int)std::max<size_t>(1, (win + chunk - 1) / chunk);
+    const size_t L1 = s->L + 1, npairs = L1 * (L1 + 1) / 2;
+    dev_free(s->lag_partial);
+    s->lag_partial = nullptr;
+    return dev_alloc(&s->lag_partial, (size_t)s->k * s->lag_nchunks * npairs);
+}
+
 static int session_common_init(S *s) {
     CUDA_TRY(cudaSetDevice(s->device));
     {   // (cudaGetDeviceProperties costs milliseconds: two attribute queries, cached per device)
@@ -241,22 +278,7 @@ static int session_common_init(S *s) {
     if (pinned_get(&s->h_scal)) return 1;
     if (dev_alloc(&s->lags_dev, s->lags.size())) return 1;
     CUDA_TRY(cudaMemcpyAsync(s->lags_dev, s->lags.data(), s->lags.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
-    // lag update: chunk the window so that (chunk + mid) fp64 values fit in shared memory
-    {
-        const size_t budget = 160 * 1024 / sizeof(double);
-        if ((size_t)s->mid + 256 > budget)
-            return fail("max lag %d too large for the lag_val kernel's shared-memory staging (limit %zu)", s->mid, budget - 256);
-        size_t chunk = std::min<size_t>(4096, budget - s->mid);
-        size_t win = s->T > (size_t)s->mid ? s->T - s->mid : 0;
-        // enough CTAs to fill the machine: k * nchunks >= 2 * SMs when the window allows
-        size_t want = std::max<size_t>(1, (2 * (size_t)s->num_sms + s->k - 1) / s->k);
-        size_t c2 = std::max<size_t>(256, (win + want - 1) / want);
-        chunk = std::min(chunk, c2);
-        s->lag_chunk = (int)chunk;
-        s->lag_nchunks = (int)std::max<size_t>(1, (win + chunk - 1) / chunk);
-        const size_t L1 = s->L + 1, npairs = L1 * (L1 + 1) / 2;
-        if (dev_alloc(&s->lag_partial, (size_t)s->k * s->lag_nchunks * npairs)) return 1;
-    }
+    if (lag_plan(s)) return 1;
     if (!s->missing) {
         const size_t kk = (size_t)s->k * s->k;
         if (dev_alloc(&s->YH, tk) || dev_alloc(&s->HTH, kk) || dev_alloc(&s->WTW, kk) ||
@@ -298,6 +320,13 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
+    }
+    if (s->rolling) {   // (val_t / Yd alias R_val_t / R_Yd or the transformed window copies: freed through those)
+        dev_free(s->row_ptr); dev_free(s->col_idx); dev_free(s->R_val_t); dev_free(s->win_val_t);
+        dev_free(s->R_col_ptr); dev_free(s->R_row_idx); dev_free(s->R_val);
+        dev_free(s->col_ptr); dev_free(s->row_idx); dev_free(s->val);
+        dev_free(s->R_Yd); dev_free(s->win_Yd); dev_free(s->aff_a); dev_free(s->aff_b); dev_free(s->win_cnt);
+        dev_free(s->scan_tmp);
     }
     if (s->own_factors) { dev_free(s->W); dev_free(s->H); dev_free(s->th); }
     dev_free(s->lags_dev);
@@ -584,7 +613,7 @@ static int f_kernel_choice(int k, const V *X) {
 // scratch of the mma Gram kernel: the column-scaled factor copy and its inverse scales
 static int mma_scratch(S *s) {
     if (s->Xs) return 0;
-    if (dev_alloc(&s->Xs, std::max(s->T, s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->frow, s->T)) return 1;
+    if (dev_alloc(&s->Xs, std::max(Tcap(s), s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->frow, Tcap(s))) return 1;
     return 0;
 }
 
@@ -753,9 +782,9 @@ static int gram_prepare(S *s) {
     if (!s->missing || f_kernel_choice(s->k, s->H) == F_KERNEL_GENERIC || getenv("TRMF_B200_NO_GRAM_HV")) return 0;
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
-    const size_t need = (s->T * (size_t)s->k * s->k + s->T * (size_t)s->k) * sizeof(V);
+    const size_t need = (Tcap(s) * (size_t)s->k * s->k + Tcap(s) * (size_t)s->k) * sizeof(V);
     if (need > free_b / 2) return 0;
-    if (dev_alloc(&s->Gt, s->T * (size_t)s->k * s->k) || dev_alloc(&s->bt, s->T * (size_t)s->k)) return 1;
+    if (dev_alloc(&s->Gt, Tcap(s) * (size_t)s->k * s->k) || dev_alloc(&s->bt, Tcap(s) * (size_t)s->k)) return 1;
     s->gram_state = 1;
     return 0;
 }
@@ -1114,7 +1143,7 @@ extern "C" int trmf_b200_upload(S *s, const void *W, const void *H, const void *
 extern "C" int trmf_b200_save_factors(S *s) {
     CUDA_TRY(cudaSetDevice(s->device));
     const size_t tk = s->T * (size_t)s->k, nk = s->n * (size_t)s->k, lk = (size_t)s->L * s->k;
-    if (!s->W_sv && (dev_alloc(&s->W_sv, tk) || dev_alloc(&s->H_sv, nk) || dev_alloc(&s->th_sv, lk))) return 1;
+    if (!s->W_sv && (dev_alloc(&s->W_sv, Tcap(s) * (size_t)s->k) || dev_alloc(&s->H_sv, nk) || dev_alloc(&s->th_sv, lk))) return 1;
     CUDA_TRY(cudaMemcpyAsync(s->W_sv, s->W, tk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->H_sv, s->H, nk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
     CUDA_TRY(cudaMemcpyAsync(s->th_sv, s->th, lk * sizeof(V), cudaMemcpyDeviceToDevice, s->stream));
@@ -1248,3 +1277,4 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
 }
 
 #include "extras.cuh"   // multi-GPU (NCCL) and on-device synthetic data
+#include "rolling.cuh"  // rolling-window sessions (rolling_validate with Y resident in HBM)

@@ -60,6 +60,14 @@ def _lib(dtype):
     lib.trmf_b200_free_synth.argtypes = [POINTER(SynthDesc)]
     lib.trmf_b200_csr_from_csc.argtypes = [c_uint64, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_int32]
+    lib.trmf_b200_roll_create.restype = c_void_p
+    lib.trmf_b200_roll_create.argtypes = [P, POINTER(c_uint32), c_uint32, c_uint32, c_int32, c_int32]
+    lib.trmf_b200_roll_window.argtypes = [c_void_p, c_uint64, c_void_p, c_void_p]
+    lib.trmf_b200_upload_W_rows.argtypes = [c_void_p, c_uint64, c_uint64, c_void_p]
+    lib.trmf_b200_download_W_rows.argtypes = [c_void_p, c_uint64, c_uint64, c_void_p]
+    lib.trmf_b200_roll_nnz.restype = c_uint64
+    lib.trmf_b200_roll_nnz.argtypes = [c_void_p]
+    lib.trmf_b200_roll_export.argtypes = [c_void_p] * 7
     lib.trmf_b200_version.restype = ctypes.c_char_p
     lib.trmf_b200_value_bytes.restype = c_int32
     _proto_done.add(id(lib))
@@ -154,6 +162,27 @@ class Session(object):
         _check(self.lib, self.lib.trmf_b200_download(self.h, W.ctypes.data, H.ctypes.data, Lv.ctypes.data), "download")
         return W, H, Lv
 
+    def download_into(self, W=None, H=None, lag_val=None):
+        """Like ``download`` but into the caller's arrays (C-ordered W / H, F-ordered lag_val of this session's
+        dtype and shapes) -- e.g. the buffers of a ``trmf.Model``."""
+        def ptr(a, shape, order):
+            if a is None:
+                return None
+            assert a.dtype == self.dtype and a.shape == shape and a.flags["F_CONTIGUOUS" if order == "F" else "C_CONTIGUOUS"]
+            return a.ctypes.data
+        _check(self.lib, self.lib.trmf_b200_download(self.h, ptr(W, (self.T, self.k), "C"), ptr(H, (self.n, self.k), "C"),
+                                                     ptr(lag_val, (self.L, self.k), "F")), "download")
+
+    def upload_W_rows(self, row0, rows):
+        rows = np.ascontiguousarray(rows, dtype=self.dtype)
+        assert rows.ndim == 2 and rows.shape[1] == self.k
+        _check(self.lib, self.lib.trmf_b200_upload_W_rows(self.h, int(row0), rows.shape[0], rows.ctypes.data), "upload_W_rows")
+
+    def download_W_rows(self, row0, nrows):
+        out = np.empty((int(nrows), self.k), dtype=self.dtype, order="C")
+        _check(self.lib, self.lib.trmf_b200_download_W_rows(self.h, int(row0), int(nrows), out.ctypes.data), "download_W_rows")
+        return out
+
     def upload(self, W=None, H=None, lag_val=None):
         keep = []
 
@@ -175,6 +204,72 @@ class Session(object):
             self.close()
         except Exception:
             pass
+
+
+class RollingSession(Session):
+    """Y resident in HBM across the windows of ``rolling_validate`` (reference trmf.py:303-329).
+
+    ``RollingSession(Y, lag_set, k, missing)`` uploads Y once -- every time stamp any window trains on; a scipy
+    sparse matrix (one orientation crosses PCIe, the other is derived on the device) or a dense array (made
+    C-contiguous: a prefix of the time axis must be contiguous).  ``window(T_w, scale, offset)`` then makes all
+    ``Session`` calls operate on ``Y[:T_w]`` -- optionally through the per-series affine map of the reference's
+    ``NormalizedTransform.preprocess`` -- without touching the host copy of Y again; factors of the previous
+    window stay in place and ``upload_W_rows`` appends the warm-start rows of W."""
+
+    def __init__(self, Y, lag_set, k, missing=True, dtype=None, device=0, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1):
+        dtype = np.dtype(dtype if dtype is not None else Y.dtype)
+        self.dtype = dtype
+        self.lib = lib = _lib(dtype)
+        if lib.trmf_b200_device_count() <= 0:
+            raise RuntimeError("trmf: no CUDA device visible; this solver is GPU-only (B200, sm_100a)")
+        self.lag_set = np.ascontiguousarray(np.sort(np.asarray(lag_set)), dtype=np.uint32)
+        if isinstance(Y, PyMatrix):
+            self.pyY = Y
+        elif isinstance(Y, np.ndarray):
+            self.pyY = PyMatrix(np.ascontiguousarray(Y), dtype, major="row")
+        else:
+            self.pyY = PyMatrix(Y, dtype, twin=False)
+        self.T_cap = self.T = int(self.pyY.rows)
+        self.n = int(self.pyY.cols)
+        self.k = int(k)
+        self.L = len(self.lag_set)
+        self.h = lib.trmf_b200_roll_create(byref(self.pyY), self.lag_set.ctypes.data_as(POINTER(c_uint32)), self.L,
+                                           self.k, int(bool(missing)), device)
+        if not self.h:
+            raise RuntimeError("trmf (CUDA) roll_create failed: " + lib.trmf_b200_last_error().decode())
+        self.pyY = None   # the device holds Y now; let the host marshalling copies go
+        self.set_params(lambdaI, lambdaAR, lambdaLag)
+
+    def window(self, T_w, scale=None, offset=None):
+        """Train on ``Y[:T_w]`` from now on; ``scale`` / ``offset``: n values each, ``y -> y*scale[j] + offset[j]``."""
+        keep = []
+
+        def ptr(a):
+            if a is None:
+                return None
+            a = np.ascontiguousarray(np.asarray(a).reshape(-1), dtype=self.dtype)
+            assert a.shape[0] == self.n
+            keep.append(a)
+            return a.ctypes.data
+        _check(self.lib, self.lib.trmf_b200_roll_window(self.h, int(T_w), ptr(scale), ptr(offset)), "roll_window")
+        self.T = int(T_w)
+
+    @property
+    def nnz(self):
+        return int(self.lib.trmf_b200_roll_nnz(self.h))
+
+    def export_window(self):
+        """(row_ptr, col_idx, val_t, col_ptr, row_idx, val) of the current window, as the device holds them."""
+        nz = self.nnz
+        row_ptr = np.empty(self.T + 1, dtype=np.uint64)
+        col_ptr = np.empty(self.n + 1, dtype=np.uint64)
+        col_idx = np.empty(nz, dtype=np.uint32)
+        row_idx = np.empty(nz, dtype=np.uint32)
+        val_t = np.empty(nz, dtype=self.dtype)
+        val = np.empty(nz, dtype=self.dtype)
+        _check(self.lib, self.lib.trmf_b200_roll_export(self.h, row_ptr.ctypes.data, col_idx.ctypes.data, val_t.ctypes.data,
+                                                        col_ptr.ctypes.data, row_idx.ctypes.data, val.ctypes.data), "roll_export")
+        return row_ptr, col_idx, val_t, col_ptr, row_idx, val
 
 
 def csr_from_csc(csc, dtype=None, device=0):

@@ -316,13 +316,26 @@ class Metrics(collections.namedtuple("Metrics", _METRIC_FIELDS)):
 
 
 def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5, lambdaAR=50, lambdaLag=0.5,
-                     max_iter=20, missing=True, threshold=0, transform=None, threads=16, verbose=0, seed=0):
+                     max_iter=20, missing=True, threshold=0, transform=None, threads=16, verbose=0, seed=0,
+                     resident=None, _sessions=None):
     """Rolling-origin evaluation (reference trmf.py:303-329): ``nr_windows``
     successive fits, each warm-started from the previous one and forecasting the
     next ``window_size`` time stamps.  ``missing=True`` turns exact zeros of the
-    dense slice into unobserved entries (``csr_matrix(Y_trn)``)."""
+    dense slice into unobserved entries (``csr_matrix(Y_trn)``).
+
+    ``resident`` (additive): keep Y in HBM across the windows instead of
+    converting and uploading the growing prefix for every fit (``_rolling_resident``
+    below).  Same models, forecasts and metrics, bit for bit; default on for a
+    dense float32/float64 ``Y`` when ``verbose == 0`` (the per-window path prints
+    the reference's parameter dump), ``TRMF_B200_ROLLING_HOST=1`` turns it off."""
     T, n = Y.shape[0], Y.shape[1]
     assert T > nr_windows * window_size
+    if resident is None:
+        resident = (verbose == 0 and isinstance(Y, np.ndarray) and Y.dtype in (np.float32, np.float64)
+                    and not os.environ.get("TRMF_B200_ROLLING_HOST"))
+    if resident:
+        return _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR, lambdaLag, max_iter, missing,
+                                 threshold, transform, seed, sessions=_sessions)
     horizon = nr_windows * window_size
     trueY = Y[-horizon:, :]
     forecastY = np.zeros((horizon, n), dtype=Y.dtype, order="C")
@@ -340,21 +353,87 @@ def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5
     return Metrics.generate(trueY, forecastY, missing=missing)
 
 
+def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR, lambdaLag, max_iter, missing,
+                      threshold, transform, seed, models_out=None, sessions=None):
+    """``rolling_validate`` with Y resident on the device (``session.RollingSession``).
+
+    The host keeps doing what the reference's loop does around ``train`` --
+    ``Model.initialize`` (RNG stream, AR roll-out warm start, a fresh
+    ``NormalizedTransform`` per window: trmf.py:222-251) and ``Model.forecast``
+    (trmf.py:184-193) -- on the same NumPy expressions, so every window starts
+    from the same bits.  What no longer happens per window: ``csr_matrix(Y_trn)``,
+    the PyMatrix conversions, the upload of Y and of the factors (W[:T_prev], H
+    and lag_val are already in HBM, bit-identical to what would be sent; only the
+    ``window_size`` rolled-out rows of W cross PCIe), session set-up.
+
+    ``sessions`` (a dict owned by the caller, e.g. ``grid_search``): sessions are
+    parked there under (k, missing, resident length, lag set) instead of being
+    closed, so that further calls over the same Y with other regularisation
+    weights / iteration counts reuse the resident copy."""
+    from .session import RollingSession   # (session imports this module)
+    T, n = Y.shape[0], Y.shape[1]
+    horizon = nr_windows * window_size
+    trueY = Y[-horizon:, :]
+    forecastY = np.zeros((horizon, n), dtype=Y.dtype, order="C")
+    Y_res = Y[:T - window_size, :]        # the longest prefix any window trains on
+    key = (int(k), bool(missing), Y_res.shape[0], tuple(sorted(int(l) for l in lag_set)), np.dtype(Y.dtype).str)
+    sess = sessions.pop(key, None) if sessions is not None else None
+    if sess is None:
+        sess = RollingSession(smat.csr_matrix(Y_res) if missing else Y_res, lag_set, k, missing=missing, dtype=Y.dtype)
+    sess.set_params(lambdaI, lambdaAR, lambdaLag)
+    done = False
+    try:
+        prev_model = None
+        for w in range(nr_windows):
+            trn_end = T - (nr_windows - w) * window_size
+            # the dense slice stands in for csr_matrix(Y_trn): initialize() only takes its shape, dtype and
+            # NormalizedTransform statistics, which the reference computes on toarray() anyway (trmf.py:84)
+            curr_model = Model.initialize(Y[:trn_end, :], lag_set, k, seed=seed, warm_start_model=prev_model,
+                                          transform=transform)
+            tr = curr_model.transform
+            sess.window(trn_end, None if tr is None else tr.a, None if tr is None else tr.b)
+            if prev_model is None:
+                sess.upload(W=curr_model.W, H=curr_model.H, lag_val=curr_model.lag_val)
+            else:
+                sess.upload_W_rows(prev_model.m, curr_model.W[prev_model.m:, :])
+            sess.train(max_iter=max_iter, period_W=1, period_H=1, period_Lag=2, verbose=0)
+            sess.download_into(curr_model.W, curr_model.H, curr_model.lag_val)
+            curr_model.forecast(window_size, Ynew=forecastY[w * window_size:(w + 1) * window_size, :], threshold=threshold)
+            if models_out is not None:
+                models_out.append(curr_model)
+            prev_model = curr_model
+        done = True
+    finally:
+        if done and sessions is not None:
+            sessions[key] = sess
+        else:
+            sess.close()
+    return Metrics.generate(trueY, forecastY, missing=missing)
+
+
 def grid_search(Y, lag_set, grid_params, pkl_file=None, **kw_args):
     """Exhaustive search over ``grid_params`` (dict name -> list of values),
-    ranking by ``m_nd`` (reference trmf.py:331-346)."""
+    ranking by ``m_nd`` (reference trmf.py:331-346).  Every grid point is one
+    ``rolling_validate``; on the resident path (its default for a dense float
+    array) the grid points share one copy of Y in HBM per (k, window_size,
+    missing) instead of re-ingesting it nr_windows times per point."""
     results = []
     best = Metrics.default()
     names = list(grid_params.keys())
-    for combo in itertools.product(*[grid_params[name] for name in names]):
-        kws = dict(kw_args)
-        kws.update(zip(names, combo))
-        metrics = rolling_validate(Y, lag_set, **kws)
-        results.append({"kws": kws, "metrics": metrics})
-        if metrics.m_nd < best.m_nd:
-            best = metrics
-            print(metrics, dict(zip(names, combo)))
-        if pkl_file is not None:
-            with open(pkl_file, "wb") as fh:
-                pickle.dump(results, fh)
+    sessions = {}
+    try:
+        for combo in itertools.product(*[grid_params[name] for name in names]):
+            kws = dict(kw_args)
+            kws.update(zip(names, combo))
+            metrics = rolling_validate(Y, lag_set, _sessions=sessions, **kws)
+            results.append({"kws": kws, "metrics": metrics})
+            if metrics.m_nd < best.m_nd:
+                best = metrics
+                print(metrics, dict(zip(names, combo)))
+            if pkl_file is not None:
+                with open(pkl_file, "wb") as fh:
+                    pickle.dump(results, fh)
+    finally:
+        for sess in sessions.values():
+            sess.close()
     return results, best

@@ -182,6 +182,30 @@ int  trmf_b200_copy_to_host(void *dst_host, const void *src_device, uint64_t byt
 int  trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *row_idx,
                             const void *val, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, int32_t device);
 
+/* ---- rolling-window sessions (replaces the per-window re-ingest of the reference's
+ *      rolling_validate, python/trmf/trmf.py:303-329) ----
+ * trmf_b200_roll_create uploads Y ONCE (all the time stamps any window will train on: sparse with either or both
+ * orientations, or dense ROW-major) and allocates factors and work space for the full length.  The factors start as
+ * zeros: send them with trmf_b200_upload() after the first trmf_b200_roll_window().
+ * trmf_b200_roll_window(s, T_w, scale, offset) makes the session train on the prefix Y[:T_w]: by-time CSR = prefix of
+ * the resident one, by-series CSC re-compacted on the device (bit-identical to a fresh ingest of Y[:T_w]).  scale /
+ * offset (host arrays of n values of the library's ValueType, or both NULL) apply the reference's
+ * NormalizedTransform.preprocess (trmf.py:90-92) per series, y*scale[j] + offset[j], two roundings like NumPy.
+ * W[:T_prev], H and lag_val of the previous window stay in place (the warm start of trmf.py:237-246); the host sends
+ * the new rows of W with trmf_b200_upload_W_rows().  All other session calls (train, phases, download, stat) work
+ * on the current window. */
+trmf_b200_session *trmf_b200_roll_create(const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size, uint32_t k,
+                                         int32_t missing, int32_t device);
+int trmf_b200_roll_window(trmf_b200_session *s, uint64_t T_window, const void *scale, const void *offset);
+/* rows [row0, row0+nrows) of W from / to a host buffer of nrows x k values (any session) */
+int trmf_b200_upload_W_rows(trmf_b200_session *s, uint64_t row0, uint64_t nrows, const void *src);
+int trmf_b200_download_W_rows(trmf_b200_session *s, uint64_t row0, uint64_t nrows, void *dst);
+/* the current window's matrices back on the host (parity tests of the windowed index work); sparse rolling sessions;
+ * any pointer may be NULL; row_ptr T_w+1, col_ptr n+1, the others trmf_b200_roll_nnz() elements */
+uint64_t trmf_b200_roll_nnz(trmf_b200_session *s);
+int trmf_b200_roll_export(trmf_b200_session *s, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, uint64_t *col_ptr,
+                          uint32_t *row_idx, void *val);
+
 #ifdef __cplusplus
 }
 #endif

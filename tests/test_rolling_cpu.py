@@ -1,0 +1,169 @@
+"""Host logic of the device-resident ``rolling_validate``, checked on the CPU.
+
+The resident path (``trmf.trmf._rolling_resident``) must hand every window the same bits the reference's loop
+(python/trmf/trmf.py:303-329) would: same initial factors, same warm-start rows, same per-window transform.  Here the
+CUDA session is replaced by a stand-in that keeps "device" state across windows like ``session.RollingSession`` does
+and runs the NumPy oracle on it, and ``trmf.train`` is replaced by the same oracle, so both paths must agree exactly.
+The real session is exercised by tests/test_rolling_gpu.py.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import trmf
+import trmf.trmf as tmod
+import trmf.session as smod
+from oracle import trmf_numpy as tn
+
+
+def oracle_train(Y, model, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1, max_iter=10, period_W=1, period_H=1, period_Lag=2,
+                 threads=1, missing=False, verbose=0):
+    """Stand-in for trmf.train (reference trmf.py:253-264) backed by the NumPy oracle."""
+    if model.transform is not None:
+        Y = model.transform.preprocess(Y)
+    W, H, L = tn.train(Y, model.lag_set, model.W, model.H, model.lag_val, lambdaI=lambdaI, lambdaAR=lambdaAR,
+                       lambdaLag=lambdaLag, max_iter=max_iter, period_W=period_W, period_H=period_H, period_Lag=period_Lag,
+                       missing=missing)
+    model.W[:] = W; model.H[:] = H; model.lag_val[:] = L
+    return model
+
+
+class FakeRollingSession(object):
+    """Same interface and state model as session.RollingSession, oracle arithmetic."""
+    log = []
+
+    def __init__(self, Y, lag_set, k, missing=True, dtype=None, device=0, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1):
+        self.Y = Y.tocsr() if sps.issparse(Y) else np.array(Y)
+        self.missing = missing
+        self.lag_set = np.sort(np.asarray(lag_set))
+        self.dtype = np.dtype(dtype)
+        self.T_cap, self.n = Y.shape
+        self.k = k
+        self.lams = (lambdaI, lambdaAR, lambdaLag)
+        self.W = np.full((self.T_cap, k), np.nan, dtype=self.dtype)     # stale rows must never be read
+        self.H = np.full((self.n, k), np.nan, dtype=self.dtype)
+        self.L = np.full((len(self.lag_set), k), np.nan, dtype=self.dtype, order="F")
+        self.closed = False
+        FakeRollingSession.log.append(("create", Y.shape, sps.issparse(Y)))
+
+    def set_params(self, lambdaI, lambdaAR, lambdaLag):
+        self.lams = (lambdaI, lambdaAR, lambdaLag)
+
+    def window(self, T_w, scale=None, offset=None):
+        assert 0 < T_w <= self.T_cap and not self.closed
+        self.T = T_w
+        self.a = None if scale is None else np.asarray(scale).reshape(1, -1)
+        self.b = None if offset is None else np.asarray(offset).reshape(1, -1)
+        FakeRollingSession.log.append(("window", T_w, scale is not None))
+
+    def upload(self, W=None, H=None, lag_val=None):
+        assert W.shape == (self.T, self.k)
+        self.W[:self.T] = W; self.H[:] = H; self.L[:] = lag_val
+        FakeRollingSession.log.append(("upload", W.shape[0]))
+
+    def upload_W_rows(self, row0, rows):
+        assert row0 + rows.shape[0] == self.T
+        self.W[row0:row0 + rows.shape[0]] = rows
+        FakeRollingSession.log.append(("rows", row0, rows.shape[0]))
+
+    def train(self, max_iter=10, period_W=1, period_H=1, period_Lag=2, verbose=0):
+        Y = self.Y[:self.T]
+        if self.a is not None:
+            if sps.issparse(Y):
+                Y = sps.csr_matrix(Y, copy=True)
+                Y.data = Y.data * self.a[0, Y.indices] + self.b[0, Y.indices]
+            else:
+                Y = Y * self.a + self.b
+        W, H, L = tn.train(Y, self.lag_set, self.W[:self.T], self.H, self.L, lambdaI=self.lams[0], lambdaAR=self.lams[1],
+                           lambdaLag=self.lams[2], max_iter=max_iter, period_W=period_W, period_H=period_H,
+                           period_Lag=period_Lag, missing=self.missing)
+        self.W[:self.T] = W; self.H[:] = H; self.L[:] = L
+
+    def download_into(self, W, H, lag_val):
+        W[:] = self.W[:self.T]; H[:] = self.H; lag_val[:] = self.L
+
+    def close(self):
+        self.closed = True
+
+
+def series(T, n, seed, zeros=True):
+    rng = np.random.RandomState(seed)
+    t = np.arange(T)[:, None]
+    Y = 3.0 + np.sin(2 * np.pi * t / 12.0 + rng.rand(1, n) * 6) * (1 + rng.rand(1, n)) + 0.1 * rng.randn(T, n)
+    if zeros:
+        Y[rng.rand(T, n) < 0.15] = 0.0     # missing=True reads exact zeros as unobserved (trmf.py:320-321)
+    return Y
+
+
+@pytest.mark.parametrize("missing", [True, False])
+@pytest.mark.parametrize("transform", [None, True])
+def test_resident_rolling_hands_every_window_the_same_bits(monkeypatch, missing, transform):
+    Y = series(150, 9, seed=4, zeros=missing)
+    kw = dict(k=3, window_size=6, nr_windows=4, lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=3, missing=missing,
+              threshold=0, transform=transform, seed=0)
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+    FakeRollingSession.log = []
+    host = trmf.rolling_validate(Y, [1, 2, 12], resident=False, **kw)
+    res = trmf.rolling_validate(Y, [1, 2, 12], resident=True, **kw)
+    assert host == res                                      # namedtuple of floats: exact
+    assert all(np.isfinite(v) for v in res)
+    log = FakeRollingSession.log
+    assert log[0] == ("create", (150 - 6, 9), missing)      # the longest training prefix, uploaded once
+    assert [e for e in log if e[0] == "window"] == [("window", 150 - 6 * (4 - w), transform is not None) for w in range(4)]
+    assert [e for e in log if e[0] == "upload"] == [("upload", 126)]                 # full factors: first window only
+    assert [e for e in log if e[0] == "rows"] == [("rows", 126 + 6 * w, 6) for w in range(3)]   # then window_size rows
+
+
+def test_resident_rolling_models_match_window_by_window(monkeypatch):
+    Y = series(120, 7, seed=9)
+    monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+    models = []
+    tmod._rolling_resident(Y, [1, 3], 4, 5, 3, 0.5, 5.0, 0.5, 2, True, 0, None, 0, models_out=models)
+    prev = None
+    for w, m in enumerate(models):     # the reference's loop, one window at a time
+        trn_end = 120 - (3 - w) * 5
+        Yt = sps.csr_matrix(Y[:trn_end])
+        ref = trmf.Model.initialize(Yt, [1, 3], 4, seed=0, warm_start_model=prev)
+        oracle_train(Yt, ref, lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=2, missing=True)
+        assert np.array_equal(ref.W, m.W) and np.array_equal(ref.H, m.H) and np.array_equal(ref.lag_val, m.lag_val)
+        prev = ref
+
+
+def test_grid_search_shares_the_resident_copy(monkeypatch, capsys):
+    """one upload of Y per (k, window_size, missing) for the whole grid; results as the reference's loop
+    (trmf.py:331-346) over the per-window path."""
+    Y = series(110, 6, seed=2)
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+    grid = {"lambdaAR": [5.0, 50.0], "lambdaI": [0.5, 2.0], "k": [2, 3]}
+    kw = dict(window_size=5, nr_windows=2, max_iter=2, missing=True)
+    FakeRollingSession.log = []
+    res, best = trmf.grid_search(Y, [1, 2], grid, resident=True, **kw)
+    creates = [e for e in FakeRollingSession.log if e[0] == "create"]
+    assert len(res) == 8 and len(creates) == 2                      # one session per k, not one per grid point / window
+    ref, best_ref = trmf.grid_search(Y, [1, 2], grid, resident=False, **kw)
+    assert [r["metrics"] for r in res] == [r["metrics"] for r in ref] and best == best_ref
+    assert [r["kws"]["lambdaAR"] for r in res] == [5.0, 5.0, 5.0, 5.0, 50.0, 50.0, 50.0, 50.0]
+
+
+def test_resident_default_and_switches(monkeypatch):
+    calls = []
+    monkeypatch.setattr(tmod, "_rolling_resident", lambda *a, **k: calls.append("resident") or trmf.Metrics.default())
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    Y = series(60, 4, seed=1).astype(np.float32)
+    kw = dict(k=2, window_size=4, nr_windows=2, max_iter=1)
+    trmf.rolling_validate(Y, [1, 2], **kw)
+    assert calls == ["resident"]                                    # default for a dense float array
+    trmf.rolling_validate(Y, [1, 2], resident=False, **kw)
+    monkeypatch.setenv("TRMF_B200_ROLLING_HOST", "1")
+    trmf.rolling_validate(Y, [1, 2], **kw)
+    assert calls == ["resident"]
+
+
+def test_resident_rolling_is_gpu_only():
+    """No device -> loud failure, never a host computation."""
+    if trmf.trmf._clib.clib_float32.trmf_b200_device_count() > 0:
+        pytest.skip("a GPU is visible")
+    with pytest.raises(RuntimeError, match="GPU-only"):
+        trmf.rolling_validate(series(60, 4, seed=1), [1, 2], k=2, window_size=4, nr_windows=2, max_iter=1, resident=True)

@@ -1,0 +1,137 @@
+"""GPU parity tests of the rolling-window session: ``rolling_validate`` with Y resident in HBM.
+
+What must hold (reference python/trmf/trmf.py:303-329 is the behaviour; there are no reference tests for it):
+  * index work bit-exact: the windowed by-time CSR / by-series CSC the device holds for Y[:T_w] equal the arrays the
+    reference's PyMatrix builds on the host from the same slice (rf_util.py:88-98), and the per-series affine
+    transform gives NumPy's bits;
+  * a window trains exactly like a fresh session on Y[:T_w] from the same factors (bitwise, both precisions);
+  * ``rolling_validate(resident=True)`` returns the metrics of the per-window path exactly, and the float64 forecasts
+    agree with the same loop driven by the NumPy oracle within 1e-7.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+import cases
+import trmf
+import trmf.trmf as tmod
+from trmf import session
+from trmf.rf_util import PyMatrix
+from oracle import trmf_numpy as tn
+from test_rolling_cpu import oracle_train, series
+
+pytestmark = pytest.mark.gpu
+
+LAMS = dict(lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+
+
+def sparse_case(T, n, k, lags, dens, seed, dtype):
+    p = cases.make_problem(T, n, k, lags, dens, seed)
+    Y = sps.csr_matrix((p["Ysp"].data.astype(dtype), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    return p, Y
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("fmt", ["csr", "csc"])
+def test_window_index_work_is_bit_exact(dtype, fmt):
+    p, Y = sparse_case(300, 130, 8, [1, 2, 5], 0.4, 11, dtype)
+    rs = session.RollingSession(Y.asformat(fmt), p["lags"], 8, missing=True, dtype=dtype)
+    rng = np.random.RandomState(0)
+    a = (0.5 + rng.rand(130)).astype(dtype)
+    b = rng.randn(130).astype(dtype)
+    for T_w, tr in [(300, False), (1, False), (6, True), (137, False), (137, True), (299, True), (300, True), (42, False)]:
+        rs.window(T_w, a if tr else None, b if tr else None)
+        row_ptr, col_idx, val_t, col_ptr, row_idx, val = rs.export_window()
+        Yw = Y[:T_w]
+        if tr:
+            Yw = sps.csr_matrix(Yw, copy=True)
+            Yw.data = Yw.data * a[Yw.indices] + b[Yw.indices]       # NormalizedTransform.preprocess, trmf.py:90-92
+        ref = PyMatrix(Yw, dtype).py_buf                                # host twin build, rf_util.py:88-98
+        assert rs.nnz == Yw.nnz
+        for name, got in (("row_ptr", row_ptr), ("col_idx", col_idx), ("val_t", val_t), ("col_ptr", col_ptr),
+                          ("row_idx", row_idx), ("val", val)):
+            assert got.dtype == ref[name].dtype and np.array_equal(got, ref[name]), (T_w, tr, name)
+    rs.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("mode", ["sparse", "dense"])
+@pytest.mark.parametrize("k", [8, 40])
+def test_window_trains_like_a_fresh_session(dtype, mode, k):
+    lags = [1, 7, 24]
+    p, Ysp = sparse_case(260, 150, k, lags, 0.6, 5, dtype)
+    Y = Ysp if mode == "sparse" else p["Y"].astype(dtype)
+    missing = mode == "sparse"
+    rs = session.RollingSession(Y, lags, k, missing=missing, dtype=dtype, **LAMS)
+    W0, H0, L0 = (x.astype(dtype) for x in (p["W0"], p["H0"], p["L0"]))
+    for T_w in (200, 230, 260):          # growing windows, like rolling_validate; each restarted from (W0, H0, L0)
+        rs.window(T_w)
+        rs.upload(W=W0[:T_w], H=H0, lag_val=L0)
+        rs.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
+        W, H, L = rs.download()
+        fresh = session.Session(Y[:T_w], lags, W0[:T_w], H0, L0, missing=missing, dtype=dtype, **LAMS)
+        fresh.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
+        Wf, Hf, Lf = fresh.download()
+        fresh.close()
+        assert np.array_equal(W, Wf) and np.array_equal(H, Hf) and np.array_equal(L, Lf), (T_w,)
+        Y64 = Y[:T_w].astype(np.float64)
+        Wo, Ho, Lo = tn.train(Y64, lags, W0[:T_w].astype(np.float64), H0.astype(np.float64), L0.astype(np.float64),
+                              max_iter=2, period_Lag=1, missing=missing, **LAMS)
+        tol = 1e-9 if dtype == np.float64 else 3e-5      # two iterations compound: 1e-5 per iteration
+        assert max(cases.rel(W, Wo), cases.rel(H, Ho), cases.rel(L, Lo)) < tol
+    rs.close()
+
+
+def test_partial_row_io_and_errors():
+    p, Y = sparse_case(80, 30, 4, [1, 2], 0.5, 2, np.float32)
+    rs = session.RollingSession(Y, [1, 2], 4, dtype=np.float32)
+    rs.window(60)
+    W = np.arange(60 * 4, dtype=np.float32).reshape(60, 4)
+    rs.upload(W=W, H=p["H0"].astype(np.float32), lag_val=p["L0"].astype(np.float32))
+    rs.upload_W_rows(50, -W[50:60])
+    assert np.array_equal(rs.download_W_rows(45, 15), np.vstack([W[45:50], -W[50:60]]))
+    with pytest.raises(RuntimeError, match="outside"):
+        rs.upload_W_rows(58, W[:5])
+    with pytest.raises(RuntimeError, match="outside"):
+        rs.window(81)
+    rs.close()
+    with pytest.raises(RuntimeError, match="row-major"):
+        session.RollingSession(PyMatrix(np.asfortranarray(p["Y"]), np.float64), [1, 2], 4, missing=False, dtype=np.float64)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("missing", [True, False])
+@pytest.mark.parametrize("transform", [None, True])
+def test_rolling_validate_resident_equals_per_window_path(dtype, missing, transform):
+    Y = series(400, 60, seed=3, zeros=missing).astype(dtype)
+    kw = dict(k=8, window_size=12, nr_windows=4, max_iter=6, missing=missing, transform=transform, **LAMS)
+    host = trmf.rolling_validate(Y, [1, 2, 12, 24], resident=False, **kw)
+    res = trmf.rolling_validate(Y, [1, 2, 12, 24], resident=True, **kw)
+    assert host == res
+    assert np.isfinite(res.nd) and res.nd < 1.0
+    # any memory order of Y is accepted (NumPy's own reductions round differently on it, hence not bitwise)
+    res_f = trmf.rolling_validate(np.asfortranarray(Y), [1, 2, 12, 24], resident=True, **kw)
+    assert all(abs(x - y) <= 1e-3 * abs(y) for x, y in zip(res_f, res))
+
+
+@pytest.mark.parametrize("missing", [True, False])
+def test_rolling_validate_resident_matches_the_oracle_loop(monkeypatch, missing):
+    Y = series(220, 25, seed=6, zeros=missing)
+    kw = dict(k=5, window_size=8, nr_windows=3, max_iter=3, missing=missing, transform=True, lambdaI=0.5, lambdaAR=5.0,
+              lambdaLag=0.5)
+    res = trmf.rolling_validate(Y, [1, 2, 12], resident=True, **kw)
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    ora = trmf.rolling_validate(Y, [1, 2, 12], resident=False, **kw)
+    for got, want in zip(res, ora):
+        assert abs(got - want) <= 1e-7 * abs(want)
+
+
+def test_grid_search_over_one_resident_copy():
+    """The grid points of grid_search (trmf.py:331-346) reuse one rolling session: same results as fresh ones."""
+    Y = series(300, 40, seed=8).astype(np.float32)
+    grid = {"lambdaAR": [5.0, 50.0], "lambdaI": [0.5, 2.0]}
+    kw = dict(k=8, window_size=10, nr_windows=3, max_iter=4, missing=True, transform=True)
+    res, best = trmf.grid_search(Y, [1, 2, 12], grid, resident=True, **kw)
+    ref, best_ref = trmf.grid_search(Y, [1, 2, 12], grid, resident=False, **kw)
+    assert [r["metrics"] for r in res] == [r["metrics"] for r in ref] and best == best_ref
+    assert len({r["metrics"].nd for r in res}) == 4          # the weights did reach the device
