@@ -87,6 +87,49 @@ __global__ void roll_affine_dense_kernel(const VT *__restrict__ Y, uint64_t cell
     }
 }
 
+// ---- dense -> sparse at ingest: the non-zero cells of a row-major T x n array as a canonical CSR, i.e. what the
+// reference's rolling_validate gets from `csr_matrix(Y_trn)` when missing=True (trmf.py:320-321: exact zeros are
+// unobserved; -0.0 counts as zero, NaN as a value -- both as scipy decides them).  One warp per time stamp.
+template <typename VT>
+__global__ void roll_dense_count_kernel(const VT *__restrict__ Y, uint64_t T, uint64_t n, uint64_t *__restrict__ cnt /* T + 1 */) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    if (warp == 0 && lane == 0) cnt[T] = 0;
+    for (uint64_t i = warp; i < T; i += nwarps) {
+        const VT *row = Y + i * n;
+        unsigned c = 0;
+        for (uint64_t j = lane; j < n; j += 32) c += row[j] != (VT)0 ? 1u : 0u;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(FULL_MASK, c, o);
+        if (lane == 0) cnt[i] = c;
+    }
+}
+
+template <typename VT>
+__global__ void roll_dense_fill_kernel(const VT *__restrict__ Y, uint64_t T, uint64_t n, const uint64_t *__restrict__ row_ptr,
+                                       uint32_t *__restrict__ col_idx, VT *__restrict__ val_t) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = warp; i < T; i += nwarps) {
+        const VT *row = Y + i * n;
+        uint64_t pos = row_ptr[i];
+        for (uint64_t j0 = 0; j0 < n; j0 += 32) {       // ballot keeps the columns of a time stamp in ascending order
+            const uint64_t j = j0 + lane;
+            const VT y = j < n ? row[j] : (VT)0;
+            const bool keep = j < n && y != (VT)0;
+            const unsigned m = __ballot_sync(FULL_MASK, keep);
+            if (keep) {
+                const uint64_t e = pos + __popc(m & ((1u << lane) - 1u));
+                col_idx[e] = (uint32_t)j;
+                val_t[e] = y;
+            }
+            pos += __popc(m);
+        }
+    }
+}
+
 static int roll_window_impl(S *s, uint64_t Tw, const void *a_host, const void *b_host);
 
 static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size, uint32_t k, int missing,
@@ -98,6 +141,7 @@ static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     s->n = Y->cols;
     s->k = (int)k;
     s->missing = missing != 0;
+    bool dense_to_sparse = false;
     if (k < 1 || k > 128) return fail("rank k = %u outside the supported range 1..128", k);
     if (s->T == 0 || s->n == 0) return fail("rolling session needs a non-empty Y");
     if (s->T >= (1ull << 32) || s->n >= (1ull << 32)) return fail("T and n must fit uint32 indices");
@@ -106,8 +150,10 @@ static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         s->sparse_storage = true;
         s->nnz = s->R_nnz = Y->nnz;
     } else if (Y->type == TRMF_DENSE_ROWMAJOR) {
-        if (s->missing) return fail("missing != 0 requires a sparse Y (the reference asserts in get_sparse(), trmf.cpp:229)");
-        s->sparse_storage = false;
+        // missing != 0 with a dense array: its non-zero cells are the observations (rolling_validate's
+        // csr_matrix(Y_trn), trmf.py:320-321), sparsified on the device below
+        dense_to_sparse = s->missing;
+        s->sparse_storage = s->missing;
         s->dense_type = Y->type;
         s->nnz = s->T * s->n;
     } else if (Y->type == TRMF_DENSE_COLMAJOR) {
@@ -123,17 +169,40 @@ static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     CUDA_TRY(cudaMemsetAsync(s->H, 0, nk * sizeof(V), s->stream));
     CUDA_TRY(cudaMemsetAsync(s->th, 0, lk * sizeof(V), s->stream));
     if (s->sparse_storage) {
+        const size_t scan_items = std::max(s->T, s->n) + 1;
+        if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->win_cnt, scan_items)) return 1;
+        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, s->scan_tmp_bytes, s->win_cnt, s->row_ptr, (int64_t)scan_items, s->stream));
+        CUDA_TRY(cudaMallocAsync(&s->scan_tmp, s->scan_tmp_bytes ? s->scan_tmp_bytes : 1, s->stream));
+        V *dense = nullptr;
+        if (dense_to_sparse) {
+            const unsigned grid = (unsigned)(s->num_sms * 8);
+            if (dev_alloc(&dense, s->T * s->n)) return 1;
+            CUDA_TRY(cudaMemcpyAsync(dense, Y->val, s->T * s->n * sizeof(V), cudaMemcpyHostToDevice, s->stream));
+            LAUNCH(s, roll_dense_count_kernel<V>, grid, 256, 0, dense, (uint64_t)s->T, (uint64_t)s->n, s->win_cnt);
+            CUDA_TRY(cub::DeviceScan::ExclusiveSum(s->scan_tmp, s->scan_tmp_bytes, s->win_cnt, s->row_ptr, (int64_t)(s->T + 1), s->stream));
+            s->launches++;
+            uint64_t total = 0;
+            CUDA_TRY(cudaMemcpyAsync(&total, s->row_ptr + s->T, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));
+            CUDA_TRY(cudaStreamSynchronize(s->stream));
+            s->nnz = s->R_nnz = total;
+        }
         const size_t nnz = s->R_nnz;
-        const bool have_csr = Y->row_ptr && (nnz == 0 || (Y->col_idx && Y->val_t));
-        const bool have_csc = Y->col_ptr && (nnz == 0 || (Y->row_idx && Y->val));
+        const bool have_csr = dense_to_sparse || (Y->row_ptr && (nnz == 0 || (Y->col_idx && Y->val_t)));
+        const bool have_csc = !dense_to_sparse && Y->col_ptr && (nnz == 0 || (Y->row_idx && Y->val));
         if (!have_csr && !have_csc) return fail("sparse Y carries neither a complete CSR nor a complete CSC half");
-        if (dev_alloc(&s->row_ptr, s->T + 1) || dev_alloc(&s->col_idx, nnz) || dev_alloc(&s->R_val_t, nnz) ||
+        if (dev_alloc(&s->col_idx, nnz) || dev_alloc(&s->R_val_t, nnz) ||
             dev_alloc(&s->R_col_ptr, s->n + 1) || dev_alloc(&s->R_row_idx, nnz) || dev_alloc(&s->R_val, nnz) ||
-            dev_alloc(&s->col_ptr, s->n + 1) || dev_alloc(&s->row_idx, nnz) || dev_alloc(&s->val, nnz) ||
-            dev_alloc(&s->win_cnt, s->n + 1))
+            dev_alloc(&s->col_ptr, s->n + 1) || dev_alloc(&s->row_idx, nnz) || dev_alloc(&s->val, nnz))
             return 1;
-        // one orientation crosses PCIe, the other is the stable device transpose (ingest.cuh), like any session
-        if (have_csc) {
+        // one orientation crosses PCIe (or comes out of the dense array), the other is the stable device transpose
+        // (ingest.cuh), like any session
+        if (dense_to_sparse) {
+            LAUNCH(s, roll_dense_fill_kernel<V>, (unsigned)(s->num_sms * 8), 256, 0, dense, (uint64_t)s->T, (uint64_t)s->n, s->row_ptr,
+                   s->col_idx, s->R_val_t);
+            dev_free(dense);
+            CUDA_TRY(csr_from_csc_device<V>(s->stream, s->num_sms, s->n, s->T, nnz, s->row_ptr, s->col_idx, s->R_val_t, s->R_col_ptr,
+                                            s->R_row_idx, s->R_val));
+        } else if (have_csc) {
             CUDA_TRY(cudaMemcpyAsync(s->R_col_ptr, Y->col_ptr, (s->n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, s->stream));
             if (nnz) {
                 CUDA_TRY(cudaMemcpyAsync(s->R_row_idx, Y->row_idx, nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->stream));
@@ -151,8 +220,6 @@ static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                                             s->R_row_idx, s->R_val));
         }
         s->launches += 5;
-        CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, s->scan_tmp_bytes, s->win_cnt, s->col_ptr, (int64_t)(s->n + 1), s->stream));
-        CUDA_TRY(cudaMallocAsync(&s->scan_tmp, s->scan_tmp_bytes ? s->scan_tmp_bytes : 1, s->stream));
     } else {
         if (dev_alloc(&s->R_Yd, s->T * s->n)) return 1;
         CUDA_TRY(cudaMemcpyAsync(s->R_Yd, Y->val, s->T * s->n * sizeof(V), cudaMemcpyHostToDevice, s->stream));

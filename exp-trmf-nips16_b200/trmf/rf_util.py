@@ -71,7 +71,7 @@ class PyMatrix(ctypes.Structure):
         ("type", ctypes.c_int32),
     ]
 
-    def __init__(self, A, dtype=np.float32, major=None, twin=True):
+    def __init__(self, A, dtype=np.float32, major=None, twin=True, copy=True):
         """``major`` ('row' / 'col', optional, additive to the reference signature)
         settles the type tag of arrays that are both C- and F-contiguous (a
         single row or column, e.g. W with k == 1), which the reference would tag
@@ -83,7 +83,12 @@ class PyMatrix(ctypes.Structure):
         otherwise) and leaves the other three pointers NULL: the CUDA library
         derives the missing half on the device, bit-identically
         (``csrc/ingest.cuh``).  ``trmf.train`` uses this; such a PyMatrix is not
-        valid input for the reference's own core."""
+        valid input for the reference's own core.
+
+        ``copy`` (additive): the reference always copies a dense array
+        (``A.astype(dtype)``, rf_util.py:122).  ``copy=False`` adopts ``A`` itself
+        when it already has the dtype and is contiguous -- for read-only inputs
+        such as a large Y."""
         super().__init__()
         if A is None:
             return
@@ -116,7 +121,7 @@ class PyMatrix(ctypes.Structure):
                 buf["row_idx"] = csc.indices.astype(np.uint32)
                 buf["val"] = csc.data.astype(dtype, copy=False)
         elif isinstance(A, np.ndarray):
-            arr = A.astype(dtype)   # order='K': keeps the caller's memory layout
+            arr = A.astype(dtype, copy=copy)   # order='K': keeps the caller's memory layout
             if not (arr.flags.c_contiguous or arr.flags.f_contiguous):
                 arr = np.ascontiguousarray(arr)
             buf["val"] = arr

@@ -211,7 +211,9 @@ class RollingSession(Session):
 
     ``RollingSession(Y, lag_set, k, missing)`` uploads Y once -- every time stamp any window trains on; a scipy
     sparse matrix (one orientation crosses PCIe, the other is derived on the device) or a dense array (made
-    C-contiguous: a prefix of the time axis must be contiguous).  ``window(T_w, scale, offset)`` then makes all
+    C-contiguous: a prefix of the time axis must be contiguous).  A dense array with ``missing=True`` is
+    sparsified on the device: its non-zero cells are the observations, exactly the ``csr_matrix(Y_trn)`` of the
+    reference's loop (trmf.py:320-321) without the host conversion.  ``window(T_w, scale, offset)`` then makes all
     ``Session`` calls operate on ``Y[:T_w]`` -- optionally through the per-series affine map of the reference's
     ``NormalizedTransform.preprocess`` -- without touching the host copy of Y again; factors of the previous
     window stay in place and ``upload_W_rows`` appends the warm-start rows of W."""
@@ -226,7 +228,7 @@ class RollingSession(Session):
         if isinstance(Y, PyMatrix):
             self.pyY = Y
         elif isinstance(Y, np.ndarray):
-            self.pyY = PyMatrix(np.ascontiguousarray(Y), dtype, major="row")
+            self.pyY = PyMatrix(np.ascontiguousarray(Y), dtype, major="row", copy=False)
         else:
             self.pyY = PyMatrix(Y, dtype, twin=False)
         self.T_cap = self.T = int(self.pyY.rows)

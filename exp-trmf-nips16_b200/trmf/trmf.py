@@ -361,7 +361,8 @@ def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR,
     ``Model.initialize`` (RNG stream, AR roll-out warm start, a fresh
     ``NormalizedTransform`` per window: trmf.py:222-251) and ``Model.forecast``
     (trmf.py:184-193) -- on the same NumPy expressions, so every window starts
-    from the same bits.  What no longer happens per window: ``csr_matrix(Y_trn)``,
+    from the same bits.  What no longer happens per window (or at all, on the
+    host): ``csr_matrix(Y_trn)`` -- 2-4 s for a 10 000 x 10 000 array --,
     the PyMatrix conversions, the upload of Y and of the factors (W[:T_prev], H
     and lag_val are already in HBM, bit-identical to what would be sent; only the
     ``window_size`` rolled-out rows of W cross PCIe), session set-up.
@@ -379,7 +380,8 @@ def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR,
     key = (int(k), bool(missing), Y_res.shape[0], tuple(sorted(int(l) for l in lag_set)), np.dtype(Y.dtype).str)
     sess = sessions.pop(key, None) if sessions is not None else None
     if sess is None:
-        sess = RollingSession(smat.csr_matrix(Y_res) if missing else Y_res, lag_set, k, missing=missing, dtype=Y.dtype)
+        # dense in both modes: with missing=True the device keeps the non-zero cells, i.e. csr_matrix(Y_res)
+        sess = RollingSession(Y_res, lag_set, k, missing=missing, dtype=Y.dtype)
     sess.set_params(lambdaI, lambdaAR, lambdaLag)
     done = False
     try:

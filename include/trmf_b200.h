@@ -185,7 +185,9 @@ int  trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t
 /* ---- rolling-window sessions (replaces the per-window re-ingest of the reference's
  *      rolling_validate, python/trmf/trmf.py:303-329) ----
  * trmf_b200_roll_create uploads Y ONCE (all the time stamps any window will train on: sparse with either or both
- * orientations, or dense ROW-major) and allocates factors and work space for the full length.  The factors start as
+ * orientations, or dense ROW-major) and allocates factors and work space for the full length.  A dense Y with
+ * missing != 0 is sparsified on the device: its non-zero cells become the observed entries, bit-identical to the
+ * `csr_matrix(Y_trn)` of the reference's loop (trmf.py:320-321).  The factors start as
  * zeros: send them with trmf_b200_upload() after the first trmf_b200_roll_window().
  * trmf_b200_roll_window(s, T_w, scale, offset) makes the session train on the prefix Y[:T_w]: by-time CSR = prefix of
  * the resident one, by-series CSC re-compacted on the device (bit-identical to a fresh ingest of Y[:T_w]).  scale /

@@ -34,6 +34,8 @@ class FakeRollingSession(object):
 
     def __init__(self, Y, lag_set, k, missing=True, dtype=None, device=0, lambdaI=0.1, lambdaAR=0.1, lambdaLag=0.1):
         self.Y = Y.tocsr() if sps.issparse(Y) else np.array(Y)
+        if missing and not sps.issparse(Y):
+            self.Y = sps.csr_matrix(self.Y)      # the device keeps the non-zero cells (trmf.py:320-321)
         self.missing = missing
         self.lag_set = np.sort(np.asarray(lag_set))
         self.dtype = np.dtype(dtype)
@@ -109,7 +111,7 @@ def test_resident_rolling_hands_every_window_the_same_bits(monkeypatch, missing,
     assert host == res                                      # namedtuple of floats: exact
     assert all(np.isfinite(v) for v in res)
     log = FakeRollingSession.log
-    assert log[0] == ("create", (150 - 6, 9), missing)      # the longest training prefix, uploaded once
+    assert log[0] == ("create", (150 - 6, 9), False)        # the longest training prefix, uploaded once, as it is
     assert [e for e in log if e[0] == "window"] == [("window", 150 - 6 * (4 - w), transform is not None) for w in range(4)]
     assert [e for e in log if e[0] == "upload"] == [("upload", 126)]                 # full factors: first window only
     assert [e for e in log if e[0] == "rows"] == [("rows", 126 + 6 * w, 6) for w in range(3)]   # then window_size rows

@@ -55,6 +55,28 @@ def test_window_index_work_is_bit_exact(dtype, fmt):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(300, 130), (64, 1), (3, 77), (97, 32), (50, 1000)])
+def test_dense_array_with_missing_is_sparsified_like_csr_matrix(dtype, shape):
+    """rolling_validate's csr_matrix(Y_trn) (trmf.py:320-321) done on the device: the non-zero cells, bit-exact."""
+    T, n = shape
+    rng = np.random.RandomState(T + n)
+    Y = rng.randn(T, n).astype(dtype)
+    Y[rng.rand(T, n) < 0.3] = 0.0
+    Y[rng.rand(T, n) < 0.02] = -0.0          # negative zero is a zero for scipy too
+    Y[T // 2, :] = 0.0                       # an empty time stamp
+    Y[:, n // 2] = 0.0                       # an empty series
+    if n > 40:
+        Y[1, 30:40] = 0.0
+    rs = session.RollingSession(Y, [1, 2], 4, missing=True, dtype=dtype)
+    for T_w in sorted({T, max(1, T // 3), max(1, T - 1)}):
+        rs.window(T_w)
+        ref = PyMatrix(sps.csr_matrix(Y[:T_w]), dtype).py_buf
+        for name, got in zip(("row_ptr", "col_idx", "val_t", "col_ptr", "row_idx", "val"), rs.export_window()):
+            assert got.dtype == ref[name].dtype and np.array_equal(got, ref[name]), (T_w, name)
+    rs.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("mode", ["sparse", "dense"])
 @pytest.mark.parametrize("k", [8, 40])
 def test_window_trains_like_a_fresh_session(dtype, mode, k):

@@ -70,7 +70,7 @@ def main():
             m = trmf.rolling_validate(Y, c["lags"], resident=resident, **kw)
             times.append(time.perf_counter() - t0)
         res[name] = m
-        out[name + "_s"] = float(np.median(times[1:]))
+        out[name + "_s"] = float(np.median(times[1:] or times))
         out[name + "_s_all"] = [round(x, 4) for x in times]
     out["metrics_identical"] = bool(res["per_window"] == res["resident"])
     out["nd"] = float(res["resident"].nd)
