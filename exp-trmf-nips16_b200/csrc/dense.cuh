@@ -20,7 +20,8 @@
 template <typename TA, typename TB>
 __global__ void __launch_bounds__(256)
 gemm_partial_kernel(const TA *__restrict__ A, size_t sm, size_t sk, const TB *__restrict__ B,
-                    size_t M, int N, size_t K, size_t kchunk, double *__restrict__ Cpart) {
+                    size_t M, int N, size_t K, size_t kchunk, double *__restrict__ Cpart, const int *gate) {
+    if (gate != nullptr && *gate == 0) return;   // device-side CG control, see CG_GATE in x_update.cuh
     __shared__ double As[GT_K][GT_M + 1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *Bs = reinterpret_cast<double *>(smem_raw);   // GT_K x N
@@ -76,7 +77,8 @@ gemm_partial_kernel(const TA *__restrict__ A, size_t sm, size_t sk, const TB *__
 template <typename TO>
 __global__ void gemm_finish_kernel(const double *__restrict__ Cpart, int splits, size_t total, int N,
                                    double alpha, const V *__restrict__ addend, double beta, double diag,
-                                   TO *__restrict__ out) {
+                                   TO *__restrict__ out, const int *gate) {
+    if (gate != nullptr && *gate == 0) return;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
         double v = 0.0;
         for (int s = 0; s < splits; ++s) v += Cpart[(size_t)s * total + p];

@@ -114,6 +114,7 @@ struct trmf_b200_session {
     double *rho = nullptr;
     double *scal = nullptr, *part = nullptr;
     unsigned *ticket = nullptr;
+    int *cgctl = nullptr;         // device-side CG control: go flags of the (at most 20) CG steps of an X-update
     unsigned *queue = nullptr;    // tiled kernel: [0] series counter, [1..] per-SM CTA arrival counters
     double *h_scal = nullptr;     // pinned mirror of `scal`
 
@@ -332,7 +333,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     dev_free(s->lags_dev);
     dev_free(s->W_sv); dev_free(s->H_sv); dev_free(s->th_sv);
     dev_free(s->g); dev_free(s->s); dev_free(s->r); dev_free(s->d); dev_free(s->Hd); dev_free(s->wnew);
-    dev_free(s->rho); dev_free(s->scal); dev_free(s->part); dev_free(s->ticket); dev_free(s->queue);
+    dev_free(s->rho); dev_free(s->scal); dev_free(s->part); dev_free(s->ticket); dev_free(s->queue); dev_free(s->cgctl);
     dev_free(s->YH); dev_free(s->tmp_nk); dev_free(s->HTH); dev_free(s->WTW); dev_free(s->YtW); dev_free(s->Cpart);
     dev_free(s->lag_partial);
     pinned_put(s->h_scal);
@@ -620,15 +621,15 @@ static int mma_scratch(S *s) {
 // --------------------------------------------------------------------------
 // building blocks
 // --------------------------------------------------------------------------
-static int dot(S *s, const V *a, const V *b, size_t n, int slot) {
-    LAUNCH(s, dot_kernel, ew_grid(s, n), 256, 0, a, b, n, s->part, s->ticket, s->scal + slot);
+static int dot(S *s, const V *a, const V *b, size_t n, int slot, const int *gate = nullptr) {
+    LAUNCH(s, dot_kernel, ew_grid(s, n), 256, 0, a, b, n, s->part, s->ticket, s->scal + slot, gate);
     return 0;
 }
 
 // C (M x N, fp64 or V) = alpha * A(M x K, strided) * B (K x N row-major) + beta*addend [+ diag*I]
 template <typename TA, typename TB, typename TO>
 static int gemm(S *s, const TA *A, size_t sm, size_t sk, const TB *B, size_t M, int N, size_t K, double alpha,
-                const V *addend, double beta, double diag, TO *out) {
+                const V *addend, double beta, double diag, TO *out, const int *gate = nullptr) {
     const size_t mt = (M + GT_M - 1) / GT_M;
     size_t splits = std::max<size_t>(1, (2 * (size_t)s->num_sms + mt - 1) / mt);
     splits = std::min(splits, std::max<size_t>(1, K / (GT_K * 2)));
@@ -638,9 +639,9 @@ static int gemm(S *s, const TA *A, size_t sm, size_t sk, const TB *B, size_t M, 
     splits = (K + kchunk - 1) / kchunk;
     if (M * (size_t)N * splits > s->Cpart_elems) return fail("internal: split-K scratch too small");
     dim3 grid((unsigned)mt, (unsigned)splits);
-    LAUNCH(s, (gemm_partial_kernel<TA, TB>), grid, 256, GT_K * N * sizeof(double), A, sm, sk, B, M, N, K, kchunk, s->Cpart);
+    LAUNCH(s, (gemm_partial_kernel<TA, TB>), grid, 256, GT_K * N * sizeof(double), A, sm, sk, B, M, N, K, kchunk, s->Cpart, gate);
     LAUNCH(s, (gemm_finish_kernel<TO>), ew_grid(s, M * (size_t)N), 256, 0, s->Cpart, (int)splits, M * (size_t)N, N, alpha,
-           addend, beta, diag, out);
+           addend, beta, diag, out, gate);
     return 0;
 }
 
@@ -682,10 +683,10 @@ static LagSet lagset(const S *s) {
 }
 
 // arr_base_IX::grad / ::Hv : out = lI*v + lAR*A^T A v   (trmf.cpp:99-149)
-static int base_apply(S *s, const V *v, V *out) {
+static int base_apply(S *s, const V *v, V *out, const int *gate = nullptr) {
     const size_t tk = s->T * (size_t)s->k;
-    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k);
-    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, out, s->T, s->k, s->lambdaI, s->lambdaAR);
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k, gate);
+    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, out, s->T, s->k, s->lambdaI, s->lambdaAR, gate);
     return 0;
 }
 
@@ -708,7 +709,7 @@ static int dense_loss_init(S *s) {
 // objective value at v -> scal[slot]; dense-mode pieces are combined on the host after read_scalars()
 static int fun_launch(S *s, const V *v) {
     const size_t tk = s->T * (size_t)s->k;
-    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k);
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, v, s->th, lagset(s), s->rho, s->T, s->k, (const int *)nullptr);
     LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, v, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
     if (s->missing) {
         if (sparse_pass<MODE_FUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, v, nullptr, s->T, SC_FLOSS)) return 1;
@@ -749,10 +750,10 @@ static int grad_launch(S *s, const V *w, V *g) {
     return gemm<V, double, V>(s, w, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, g, 1.0, 0.0, g);
 }
 
-static int hv_launch(S *s, const V *d, V *Hd) {
-    if (base_apply(s, d, Hd)) return 1;
-    if (s->missing) return loss_pass<MODE_HV>(s, d, Hd);
-    return gemm<V, double, V>(s, d, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, Hd, 1.0, 0.0, Hd);
+static int hv_launch(S *s, const V *d, V *Hd, const int *gate = nullptr) {
+    if (base_apply(s, d, Hd, gate)) return 1;
+    if (s->missing) return loss_pass<MODE_HV>(s, d, Hd);   // (walks over Omega are not gated: host-controlled CG only)
+    return gemm<V, double, V>(s, d, (size_t)s->k, 1, s->HTH, s->T, s->k, (size_t)s->k, 1.0, Hd, 1.0, 0.0, Hd, gate);
 }
 
 // fun(w) and grad(w) at the same point from one walk over Omega (rf_tron.h:154-158 evaluates both
@@ -760,9 +761,9 @@ static int hv_launch(S *s, const V *d, V *Hd) {
 // share the residuals.
 static int fun_grad_launch(S *s, const V *w, V *g) {
     const size_t tk = s->T * (size_t)s->k;
-    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, s->T, s->k);
+    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, s->T, s->k, (const int *)nullptr);
     LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, w, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
-    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, g, s->T, s->k, s->lambdaI, s->lambdaAR);
+    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, w, s->th, lagset(s), s->rho, g, s->T, s->k, s->lambdaI, s->lambdaAR, (const int *)nullptr);
     if (s->world == 1) {
         if (sparse_pass<MODE_GRADFUN>(s, s->row_ptr, s->col_idx, s->val_t, s->H, w, g, s->T, SC_FLOSS, true)) return 1;
     } else {
@@ -790,27 +791,27 @@ static int gram_prepare(S *s) {
 }
 
 // loss part of the Hessian-vector product from the per-time-stamp Grams: out (+)= G_i v_i for every time stamp
-static int gram_matvec(S *s, const V *v, V *out, bool accum, double *dhd) {
+static int gram_matvec(S *s, const V *v, V *out, bool accum, double *dhd, const int *gate = nullptr) {
     const int k = s->k;
     const int WARPS = 8;
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((s->T + WARPS - 1) / WARPS, (size_t)s->num_sms * 8));
 #ifdef TRMF_F32
     if (!getenv("TRMF_B200_GENERIC_GRAM_MATVEC")) {
-#define GM_CASE(KK) case KK: LAUNCH(s, (gram_matvec4_kernel<KK, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, s->T, accum, s->part, s->ticket, dhd); return 0;
+#define GM_CASE(KK) case KK: LAUNCH(s, (gram_matvec4_kernel<KK, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, s->T, accum, s->part, s->ticket, dhd, gate); return 0;
         switch (k) { GM_CASE(8) GM_CASE(16) GM_CASE(20) GM_CASE(24) GM_CASE(32) GM_CASE(40) GM_CASE(48) default: break; }   // (k >= 56: the generic row loop)
 #undef GM_CASE
     }
 #endif
-    if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd);
-    else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd);
+    if (k <= 32) LAUNCH(s, (gram_matvec_kernel<1, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd, gate);
+    else LAUNCH(s, (gram_matvec_kernel<2, WARPS>), grid, WARPS * 32, 0, s->Gt, v, out, k, s->T, accum, s->part, s->ticket, dhd, gate);
     return 0;
 }
 
-static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd) {
+static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd, const int *gate = nullptr) {
     const size_t tk = s->T * (size_t)s->k;
-    if (base_apply(s, d, Hd)) return 1;
+    if (base_apply(s, d, Hd, gate)) return 1;
     if (s->world == 1) {
-        if (gram_matvec(s, d, Hd, true, want_dhd ? s->scal + SC_DHD : nullptr)) return 1;
+        if (gram_matvec(s, d, Hd, true, want_dhd ? s->scal + SC_DHD : nullptr, gate)) return 1;
     } else {
         if (gram_matvec(s, d, s->part_tk, false, nullptr)) return 1;
         if (dist_allreduce_v(s, s->part_tk, tk)) return 1;
@@ -898,7 +899,7 @@ extern "C" int trmf_b200_f_update(S *s) {
             if (sparse_pass<MODE_SPMM>(s, s->col_ptr, s->row_idx, s->val, s->W, nullptr, s->tmp_nk, s->n, -1)) return 1;
             // widen to fp64 for the solve
             LAUNCH(s, (gemm_finish_kernel<double>), ew_grid(s, s->n * (size_t)k), 256, 0, (const double *)nullptr, 0,
-                   s->n * (size_t)k, k, 0.0, s->tmp_nk, 1.0, 0.0, s->YtW);
+                   s->n * (size_t)k, k, 0.0, s->tmp_nk, 1.0, 0.0, s->YtW, (const int *)nullptr);
         } else {
             const bool rm = s->dense_type == TRMF_DENSE_ROWMAJOR;
             if (gemm<V, V, double>(s, s->Yd, rm ? 1 : s->T, rm ? s->n : 1, s->W, s->n, k, s->T, 1.0, nullptr, 0.0, 0.0, s->YtW)) return 1;
@@ -951,9 +952,9 @@ extern "C" int trmf_b200_x_update(S *s) {
                 rc = mma_scratch(s);
                 if (!rc && fused) {
                     // base value + base gradient first (the fused kernel adds the loss gradient on top of g)
-                    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->T, s->k);
+                    LAUNCH(s, ar_rho_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->T, s->k, (const int *)nullptr);
                     LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, s->W, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
-                    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR);
+                    LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR, (const int *)nullptr);
                     const bool one = s->world == 1;
                     rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
                                                             one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
@@ -993,7 +994,45 @@ extern "C" int trmf_b200_x_update(S *s) {
         double rTr = gg;
         size_t cg_iter = 0;
         double rnorm = gnorm;
-        while (true) {
+        // Device-side CG control: when every kernel of a CG step is one of ours on this stream (Gram-based or dense-mode
+        // Hessian products, one GPU) the steps are enqueued in chunks, each step gated by the flag the previous one left
+        // in ctl[] -- the loop head of rf_tron.h:441-456 evaluated on the device with the same fp64 scalars -- and the host
+        // looks at the scalars once per chunk instead of once per step.  Same kernels, same arguments, same order as the
+        // host-driven loop, hence bit-identical iterates.  A step that is gated off still costs its launches (~3 us per
+        // kernel, measured), a host round trip ~18 us: chunks of 4 steps bound the waste to 3 idle steps, and when the
+        // previous X-update ran into the step cap the whole budget goes out at once.  Walks over Omega and multi-GPU
+        // steps (NCCL collectives cannot be gated) keep the host loop; TRMF_B200_HOST_CG=1 forces it,
+        // TRMF_B200_CG_CHUNK=<n> sets the chunk length.
+        const bool device_cg = s->world == 1 && (!s->missing || s->gram_now) && !getenv("TRMF_B200_HOST_CG");
+        if (device_cg) {
+            if (!s->cgctl && dev_alloc(&s->cgctl, 32)) return 1;
+            CUDA_TRY(cudaMemsetAsync(s->cgctl, 0, 32 * sizeof(int), s->stream));
+            LAUNCH(s, cg_gate0_kernel, 1, 1, 0, s->scal, cur, s->cgctl, eps_cg);
+            size_t chunk = s->prev_cg >= (int)max_cg ? max_cg : 4;
+            if (const char *e = getenv("TRMF_B200_CG_CHUNK")) chunk = (size_t)std::max(1, atoi(e));
+            size_t j = 1;
+            bool go = true;
+            while (go && j <= max_cg) {
+                const size_t jend = std::min(max_cg, j + chunk - 1);
+                for (; j <= jend; ++j) {
+                    const int *gate = s->cgctl + j;
+                    if (s->missing) {
+                        if (gram_hv_launch(s, s->d, s->Hd, true, gate)) return 1;
+                    } else {
+                        if (hv_launch(s, s->d, s->Hd, gate)) return 1;
+                        if (dot(s, s->d, s->Hd, tk, SC_DHD, gate)) return 1;
+                    }
+                    LAUNCH(s, cg_step1_kernel, eg, 256, 0, s->s, s->r, s->d, s->Hd, tk, s->scal, cur, nxt, s->part, s->ticket, gate);
+                    LAUNCH(s, cg_step2_kernel, eg, 256, 0, s->d, s->r, tk, s->scal, cur, nxt, s->cgctl, (int)j);
+                    std::swap(cur, nxt);
+                }
+                if (j <= max_cg) {   // budget left: go on iff the chunk ran to its end and its last loop head said so (= ctl[j])
+                    if (read_scalars(s)) return 1;
+                    go = (size_t)s->h_scal[SC_CGIT] == jend && !(s->h_scal[SC_RNORM] <= s->h_scal[SC_CGTOL]);
+                }
+            }
+        }
+        while (!device_cg) {
             rnorm = std::sqrt(rTr);
             if (rnorm <= cgtol) break;
             if (cg_iter >= max_cg) break;
@@ -1004,8 +1043,8 @@ extern "C" int trmf_b200_x_update(S *s) {
                 if (hv_launch(s, s->d, s->Hd)) return 1;
                 if (dot(s, s->d, s->Hd, tk, SC_DHD)) return 1;
             }
-            LAUNCH(s, cg_step1_kernel, eg, 256, 0, s->s, s->r, s->d, s->Hd, tk, s->scal, cur, nxt, s->part, s->ticket);
-            LAUNCH(s, cg_step2_kernel, eg, 256, 0, s->d, s->r, tk, s->scal, cur, nxt);
+            LAUNCH(s, cg_step1_kernel, eg, 256, 0, s->s, s->r, s->d, s->Hd, tk, s->scal, cur, nxt, s->part, s->ticket, (const int *)nullptr);
+            LAUNCH(s, cg_step2_kernel, eg, 256, 0, s->d, s->r, tk, s->scal, cur, nxt, (int *)nullptr, 0);
             if (read_scalars(s)) return 1;
             rTr = s->h_scal[nxt];
             std::swap(cur, nxt);
@@ -1023,6 +1062,7 @@ extern "C" int trmf_b200_x_update(S *s) {
             if (gram_hv_launch(s, s->s, s->Hd, true)) return 1;   // scal[SC_DHD] = s'Hs
         }
         if (read_scalars(s)) return 1;
+        if (device_cg) { cg_iter = (size_t)s->h_scal[SC_CGIT]; rnorm = s->h_scal[SC_RNORM]; }
         const double gs = s->h_scal[SC_GS], sr = s->h_scal[SC_SR], snorm = std::sqrt(s->h_scal[SC_SS]);
         const double prered = -0.5 * (gs - sr);
         double fnew;

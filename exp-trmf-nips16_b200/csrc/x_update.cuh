@@ -14,6 +14,11 @@
 
 #define TRMF_MAX_LAGS 128   // block_chol_solve keeps the solution in 4 registers per lane: systems up to 128 x 128
 
+// Device-side CG control (trmf_b200_x_update): the kernels of CG step j take `gate` = the address of that step's
+// go flag and return at once when it is 0, so all <= 20 steps are enqueued without a host round trip per step.
+// gate == nullptr: always run.  The test is grid-uniform and precedes every barrier / ticket operation.
+#define CG_GATE(gate) do { if ((gate) != nullptr && *(gate) == 0) return; } while (0)
+
 struct LagSet {           // passed by value (kernel parameter space)
     int L;
     int mid;              // max lag = last element of the sorted set (trmf.cpp:79)
@@ -24,7 +29,8 @@ struct LagSet {           // passed by value (kernel parameter space)
 // Residual in fp64 exactly like the reference (trmf.cpp:110-114).  One thread
 // per (i,t), t fastest => coalesced over the row-major T x k layout.
 __global__ void ar_rho_kernel(const V *__restrict__ S, const V *__restrict__ th, LagSet ls,
-                              double *__restrict__ rho, size_t T, int k) {
+                              double *__restrict__ rho, size_t T, int k, const int *gate) {
+    CG_GATE(gate);
     const size_t total = T * (size_t)k;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
         const size_t i = p / k;
@@ -45,7 +51,8 @@ __global__ void ar_rho_kernel(const V *__restrict__ S, const V *__restrict__ th,
 // rho is stored as 0 below mid.
 __global__ void ar_apply_kernel(const V *__restrict__ S, const V *__restrict__ th, LagSet ls,
                                 const double *__restrict__ rho, V *__restrict__ out,
-                                size_t T, int k, double lambdaI, double lambdaAR) {
+                                size_t T, int k, double lambdaI, double lambdaAR, const int *gate) {
+    CG_GATE(gate);
     const size_t total = T * (size_t)k;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
         const size_t j = p / k;
@@ -179,12 +186,14 @@ static inline size_t sparse_pass_smem(int k, int warps) {
 // ---------------------------------------------------------------------------
 enum {   // slots of the device scalar block
     SC_F = 0, SC_FBASE, SC_FLOSS, SC_FNEW, SC_GG, SC_RTR, SC_DHD, SC_RNEW, SC_GS, SC_SR, SC_TMP, SC_TMP2, SC_SS,
+    SC_CGTOL, SC_RNORM, SC_CGIT,   // device-side CG control: eps_cg*||g||, the last ||r||, CG steps taken
     SC_COUNT = 16
 };
 
 // out[slot] = <a,b>
 __global__ void dot_kernel(const V *__restrict__ a, const V *__restrict__ b, size_t n,
-                           double *part, unsigned *ticket, double *out) {
+                           double *part, unsigned *ticket, double *out, const int *gate) {
+    CG_GATE(gate);
     __shared__ double red[32];
     double v = 0.0;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x)
@@ -209,9 +218,20 @@ __global__ void cg_init_kernel(const V *__restrict__ g, V *__restrict__ s, V *__
     grid_sum_commit(v, part, ticket, rtr, 1.0, red);
 }
 
+// Device-side CG control, before the first step: cgtol = eps_cg * ||g||, and step 1 runs unless ||r0|| = ||g|| <= cgtol,
+// i.e. unless g == 0 (rf_tron.h:170,441-449).  ctl[1..21] were zeroed by the host.
+__global__ void cg_gate0_kernel(double *scal, int slot, int *ctl, double eps_cg) {
+    const double gnorm = sqrt(scal[slot]);
+    scal[SC_CGTOL] = eps_cg * gnorm;
+    scal[SC_RNORM] = gnorm;
+    scal[SC_CGIT] = 0.0;
+    ctl[1] = (gnorm > 0.0 && !(gnorm <= eps_cg * gnorm)) ? 1 : 0;
+}
+
 // alpha = rTr / dHd ; s += alpha d ; r -= alpha Hd ; rnew = <r,r>   (rf_tron.h:460-493)
 __global__ void cg_step1_kernel(V *__restrict__ s, V *__restrict__ r, const V *__restrict__ d, const V *__restrict__ Hd,
-                                size_t n, double *scal, int cur, int nxt, double *part, unsigned *ticket) {
+                                size_t n, double *scal, int cur, int nxt, double *part, unsigned *ticket, const int *gate) {
+    CG_GATE(gate);
     __shared__ double red[32];
     const double alpha = scal[cur] / scal[SC_DHD];
     const V a = (V)alpha;
@@ -228,7 +248,19 @@ __global__ void cg_step1_kernel(V *__restrict__ s, V *__restrict__ r, const V *_
 
 // beta = rnew / rTr ; d += (beta-1) d ; d += r                      (rf_tron.h:494-502)
 // (rTr <- rnew is done by swapping the two scalar slots `cur`/`nxt` on the host)
-__global__ void cg_step2_kernel(V *__restrict__ d, const V *__restrict__ r, size_t n, const double *scal, int cur, int nxt) {
+// With device-side control (`ctl` != nullptr, this being step `j`): one thread also decides whether step j+1 runs --
+// the reference's loop head, rf_tron.h:441-456: stop when ||r|| <= cgtol (the step cap is the number of steps enqueued).
+__global__ void cg_step2_kernel(V *__restrict__ d, const V *__restrict__ r, size_t n, double *scal, int cur, int nxt,
+                                int *ctl, int j) {
+    if (ctl != nullptr) {
+        if (ctl[j] == 0) return;
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            const double rnorm = sqrt(scal[nxt]);
+            scal[SC_RNORM] = rnorm;
+            scal[SC_CGIT] = (double)j;
+            ctl[j + 1] = rnorm <= scal[SC_CGTOL] ? 0 : 1;
+        }
+    }
     const double beta = scal[nxt] / scal[cur];
     const V bm1 = (V)beta - (V)1;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
@@ -290,7 +322,8 @@ __global__ void tron_trial_kernel(const V *__restrict__ w, const V *__restrict__
 template <int K, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 gram_matvec4_kernel(const float *__restrict__ Gm, const float *__restrict__ S, float *__restrict__ out, size_t T, bool accum,
-                    double *part, unsigned *ticket, double *dhd) {
+                    double *part, unsigned *ticket, double *dhd, const int *gate) {
+    CG_GATE(gate);
     constexpr int NV = K * K / 4, NIT = (NV + 31) / 32, CPR = K / 4;
     __shared__ double red[32];
     __shared__ __align__(16) float sS[WARPS][K];
@@ -339,7 +372,8 @@ gram_matvec4_kernel(const float *__restrict__ Gm, const float *__restrict__ S, f
 template <int KR, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32)
 gram_matvec_kernel(const V *__restrict__ Gm, const V *__restrict__ S, V *__restrict__ out, int k, size_t T, bool accum,
-                   double *part, unsigned *ticket, double *dhd) {
+                   double *part, unsigned *ticket, double *dhd, const int *gate) {
+    CG_GATE(gate);
     __shared__ double red[32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     double dsum = 0.0;

@@ -304,3 +304,46 @@ def test_mma_gram_kernel_every_rank_ragged_and_badly_scaled(k, monkeypatch):
     well = np.asarray(mask.sum(axis=0)).ravel() >= 2 * k
     assert well.sum() > n // 2 and cases.rel(Hs[well], Hso[well]) < TOL32
     s.close()
+
+
+@pytest.mark.parametrize("dtype,mode,k", [(np.float32, "sparse", 40), (np.float32, "sparse", 8), (np.float32, "dense", 20),
+                                          (np.float64, "dense", 20), (np.float64, "sparse", 8), (np.float32, "dense_sparse_storage", 8)])
+@pytest.mark.parametrize("lam_ar", [0.5, 500.0])
+def test_device_side_cg_control_equals_the_host_driven_loop(monkeypatch, dtype, mode, k, lam_ar):
+    """The CG steps of an X-update are enqueued in chunks and gated on the device (rf_tron.h:441-456 evaluated there);
+    TRMF_B200_HOST_CG=1 is the loop with one host round trip per step.  Same kernels in the same order: identical
+    bits, identical step counts, identical accept decisions -- for early stops and for the 20-step cap."""
+    from trmf import session
+    lags = [1, 2, 3, 7, 24]
+    p = cases.make_problem(400, 160, k, lags, 0.7, 21)
+    Ysp = sps.csr_matrix((p["Ysp"].data.astype(dtype), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    Y = Ysp if mode != "dense" else p["Y"].astype(dtype)
+    missing = mode == "sparse"
+    W0, H0, L0 = (a.astype(dtype) for a in (p["W0"], p["H0"], p["L0"]))
+    out = {}
+    for variant in ("host", "default", "1", "3", "20"):      # host loop; device control with its default / given chunk lengths
+        monkeypatch.delenv("TRMF_B200_HOST_CG", raising=False)
+        monkeypatch.delenv("TRMF_B200_CG_CHUNK", raising=False)
+        if variant == "host":
+            monkeypatch.setenv("TRMF_B200_HOST_CG", "1")
+        elif variant != "default":
+            monkeypatch.setenv("TRMF_B200_CG_CHUNK", variant)
+        s = session.Session(Y, lags, W0, H0, L0, missing=missing, dtype=dtype, lambdaI=0.5, lambdaAR=lam_ar, lambdaLag=0.5)
+        trace = []
+        for it in range(3):
+            s.f_update(); s.x_update()
+            trace.append((int(s.stat("cg_iters")), int(s.stat("accepted")), s.stat("f"), s.stat("fnew"), s.stat("prered")))
+            s.lag_update()
+        out[variant] = (s.download(), trace)
+        s.close()
+    (Wh, Hh, Lh), td = out["host"]
+    for variant in ("default", "1", "3", "20"):
+        (Wd, Hd, Ld), tv = out[variant]
+        assert tv == td, variant
+        assert np.array_equal(Wd, Wh) and np.array_equal(Hd, Hh) and np.array_equal(Ld, Lh), variant
+    assert all(1 <= c <= 20 for c, *_ in td)
+    if dtype == np.float64:      # and the step counts are the oracle's
+        ref = []
+        tn.train(Y.astype(np.float64) if mode == "dense" else Ysp.astype(np.float64), lags, W0, H0, L0, lambdaI=0.5,
+                 lambdaAR=lam_ar, lambdaLag=0.5, max_iter=3, period_Lag=1, missing=missing, trace=ref)
+        assert [c for c, *_ in td] == [r["cg_iter"] for r in ref]
