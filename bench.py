@@ -117,14 +117,62 @@ def init_factors(T, n_total, k, L, dtype):
 # helpers
 # --------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md's clocks line).
+
+    The timed region of the default run is short (10 steps x 7.4 ms), less than the start-up time of an
+    `nvidia-smi -lms` process, so the samples come from NVML directly (nvidia_ml_py, in the image): a thread polls
+    every 2 ms while the main thread sits in the library's ctypes calls (GIL released).  `nvidia-smi -lms 100` runs
+    next to it as the fallback when NVML cannot be loaded."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, pci_bus_id=None):
         self.idx, self.proc, self.path = gpu_index, None, None
+        self.nvml, self.handle, self.thread, self.stop_flag = None, None, None, threading.Event()
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = None
+            if pci_bus_id:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(pci_bus_id.encode() if hasattr(pci_bus_id, "encode") else pci_bus_id)
+                except Exception:
+                    h = None
+            if h is None:
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                phys = gpu_index
+                try:
+                    if vis:
+                        phys = int(vis.split(",")[gpu_index])
+                except Exception:
+                    phys = gpu_index
+                h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.handle = pynvml, h
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv, h = self.nvml, self.handle
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons")
+        bits = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "sw_power_cap": 0x4}
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)))
+                r = int(get_reasons(h))
+                for name, bit in bits.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -136,6 +184,13 @@ class ClockSampler:
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            if self.sm:
+                out.update(sm_mhz=float(np.median(self.sm)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                           samples=len(self.sm), source="nvml, 2 ms poll")
+            return out
         if self.proc is None:
             return out
         self.proc.terminate()
@@ -158,7 +213,8 @@ class ClockSampler:
                     reasons.add(name)
         os.unlink(self.path)
         if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm),
+                       source="nvidia-smi -lms 100")
         return out
 
 
@@ -303,7 +359,12 @@ def run_b200_arm(args, cfg, rank, world, local_rank):
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank)
+    try:
+        pr = torch.cuda.get_device_properties(dev)
+        bus_id = "{:08x}:{:02x}:{:02x}.0".format(pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+    except Exception:
+        bus_id = None
+    sampler = ClockSampler(local_rank, bus_id)
     if rank == 0:
         sampler.start()
     launches0 = s.stat("kernel_launches")
