@@ -159,3 +159,30 @@ def test_pymatrix_single_orientation_leaves_the_other_half_null():
     assert both.row_ptr and both.col_ptr
     assert np.array_equal(both.py_buf["row_ptr"], csr.py_buf["row_ptr"]) and np.array_equal(both.py_buf["col_idx"], csr.py_buf["col_idx"])
     assert np.array_equal(both.py_buf["col_ptr"], csc.py_buf["col_ptr"]) and np.array_equal(both.py_buf["row_idx"], csc.py_buf["row_idx"])
+
+
+def test_header_is_plain_c_and_pymatrix_is_80_bytes(tmp_path):
+    """include/trmf_b200.h is the C ABI: it must compile as C99 (no C++ or torch types) and lay PyMatrix out like the
+    reference's POD (rf_matrix.h:3399-3415); a C caller resolves every declared entry point with dlsym."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    syms = [s for s in declared_symbols()]
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <dlfcn.h>\n#include <stdio.h>\n#include <stddef.h>\n#include "trmf_b200.h"\n'
+        "int main(int argc, char **argv) {\n"
+        "    if (sizeof(PyMatrix) != 80 || offsetof(PyMatrix, type) != 72 || offsetof(PyMatrix, val_t) != 64) return 2;\n"
+        "    void *h = dlopen(argv[1], RTLD_NOW | RTLD_LOCAL);\n"
+        '    if (!h) { fprintf(stderr, "%s\\n", dlerror()); return 3; }\n'
+        "    const char *names[] = {" + ", ".join('"%s"' % s for s in syms) + "};\n"
+        "    for (unsigned i = 0; i < sizeof names / sizeof *names; ++i)\n"
+        '        if (!dlsym(h, names[i])) { fprintf(stderr, "missing %s\\n", names[i]); return 4; }\n'
+        "    (void)argc; return 0;\n}\n")
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-D_GNU_SOURCE", "-I", os.path.join(ROOT, "include"),
+                    str(src), "-o", str(exe), "-ldl"], check=True, capture_output=True)
+    for lib in ("trmf_float32.so", "trmf_float64.so"):
+        proc = subprocess.run([str(exe), os.path.join(CORELIB, lib)], capture_output=True, text=True)
+        assert proc.returncode == 0, (lib, proc.stderr)
