@@ -317,7 +317,7 @@ class Metrics(collections.namedtuple("Metrics", _METRIC_FIELDS)):
 
 def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5, lambdaAR=50, lambdaLag=0.5,
                      max_iter=20, missing=True, threshold=0, transform=None, threads=16, verbose=0, seed=0,
-                     resident=None, _sessions=None):
+                     resident=None, _sessions=None, _models_out=None):
     """Rolling-origin evaluation (reference trmf.py:303-329): ``nr_windows``
     successive fits, each warm-started from the previous one and forecasting the
     next ``window_size`` time stamps.  ``missing=True`` turns exact zeros of the
@@ -335,7 +335,7 @@ def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5
                     and not os.environ.get("TRMF_B200_ROLLING_HOST"))
     if resident:
         return _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR, lambdaLag, max_iter, missing,
-                                 threshold, transform, seed, sessions=_sessions)
+                                 threshold, transform, seed, sessions=_sessions, models_out=_models_out)
     horizon = nr_windows * window_size
     trueY = Y[-horizon:, :]
     forecastY = np.zeros((horizon, n), dtype=Y.dtype, order="C")
@@ -349,6 +349,8 @@ def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5
         curr_model = train(Y_trn, curr_model, lambdaI=lambdaI, lambdaAR=lambdaAR, lambdaLag=lambdaLag,
                            max_iter=max_iter, missing=missing, threads=threads, verbose=verbose)
         curr_model.forecast(window_size, Ynew=forecastY[w * window_size:(w + 1) * window_size, :], threshold=threshold)
+        if _models_out is not None:     # (tests: the fitted model of every window)
+            _models_out.append(curr_model)
         prev_model = curr_model
     return Metrics.generate(trueY, forecastY, missing=missing)
 

@@ -169,3 +169,40 @@ def test_resident_rolling_is_gpu_only():
         pytest.skip("a GPU is visible")
     with pytest.raises(RuntimeError, match="GPU-only"):
         trmf.rolling_validate(series(60, 4, seed=1), [1, 2], k=2, window_size=4, nr_windows=2, max_iter=1, resident=True)
+
+
+# ---- golden vectors: the same loop with the UNMODIFIED reference core doing every fit (tests/golden/make_golden_rolling.py) ----
+ROLL_CASES = {"missing": (True, None), "missing_tr": (True, True), "full": (False, None), "full_tr": (False, True)}
+
+
+def rolling_golden():
+    from conftest import load_golden
+    g = load_golden("rolling")
+    kw = {k: v for k, v in zip(g["kw_names"], g["kw_vals"])}
+    for k in ("k", "window_size", "nr_windows", "max_iter", "seed"):
+        kw[k] = int(kw[k])
+    return g, kw, [int(l) for l in g["lags"]]
+
+
+def check_models_against_golden(g, name, models, tol):
+    import cases
+    assert len(models) == 3
+    for w, m in enumerate(models):
+        for key, got in (("W", m.W), ("H", m.H), ("L", m.lag_val)):
+            assert cases.rel(got, g["{}_w{}_{}".format(name, w, key)]) < tol, (name, w, key)
+
+
+@pytest.mark.parametrize("name", list(ROLL_CASES))
+@pytest.mark.parametrize("resident", [False, True])
+def test_rolling_loop_matches_the_reference_core(monkeypatch, name, resident):
+    """NumPy oracle as the solver, per-window loop and resident host logic alike, against fits by the compiled reference:
+    every window's factors to 1e-9, the metrics to 1e-9 -- pins warm start, transform and windowing over 3 windows."""
+    g, kw, lags = rolling_golden()
+    missing, transform = ROLL_CASES[name]
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+    models = []
+    met = trmf.rolling_validate(g[name + "_Y"], lags, missing=missing, transform=transform, resident=resident,
+                                _models_out=models, **kw)
+    check_models_against_golden(g, name, models, 1e-9)
+    assert np.allclose(np.array(list(met)), g[name + "_metrics"], rtol=1e-9, atol=0)

@@ -157,3 +157,19 @@ def test_grid_search_over_one_resident_copy():
     ref, best_ref = trmf.grid_search(Y, [1, 2, 12], grid, resident=False, **kw)
     assert [r["metrics"] for r in res] == [r["metrics"] for r in ref] and best == best_ref
     assert len({r["metrics"].nd for r in res}) == 4          # the weights did reach the device
+
+
+@pytest.mark.parametrize("name", ["missing", "missing_tr", "full", "full_tr"])
+@pytest.mark.parametrize("resident", [True, False])
+def test_rolling_validate_matches_fits_by_the_reference_core(name, resident):
+    """tests/golden/rolling.npz: the loop of trmf.py:303-329 with the compiled reference doing every fit.  The float64
+    CUDA path (resident session and per-window calls) reproduces every window's factors to 1e-8 and the metrics to
+    1e-7 (3 windows x 4 iterations from the reference's own warm starts; per-iteration parity is 1e-9)."""
+    from test_rolling_cpu import ROLL_CASES, check_models_against_golden, rolling_golden
+    g, kw, lags = rolling_golden()
+    missing, transform = ROLL_CASES[name]
+    models = []
+    met = trmf.rolling_validate(g[name + "_Y"], lags, missing=missing, transform=transform, resident=resident,
+                                _models_out=models, **kw)
+    check_models_against_golden(g, name, models, 1e-8)
+    assert np.allclose(np.array(list(met)), g[name + "_metrics"], rtol=1e-7, atol=0)
