@@ -332,6 +332,7 @@ def rolling_validate(Y, lag_set, k=40, window_size=24, nr_windows=7, lambdaI=0.5
     assert T > nr_windows * window_size
     if resident is None:
         resident = (verbose == 0 and isinstance(Y, np.ndarray) and Y.dtype in (np.float32, np.float64)
+                    and bool(__package__)      # (run as a script, like the reference allows: no package, no session module)
                     and not os.environ.get("TRMF_B200_ROLLING_HOST"))
     if resident:
         return _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR, lambdaLag, max_iter, missing,
@@ -441,3 +442,21 @@ def grid_search(Y, lag_set, grid_params, pkl_file=None, **kw_args):
         for sess in sessions.values():
             sess.close()
     return results, best
+
+
+if __name__ == "__main__":
+    # the reference's own smoke run (trmf.py:348-365): synthetic data, one fit, one rolling validation
+    def norm(x):
+        return (x * x).sum()
+
+    missing = False
+    m, n, k, lag_set = 1000, 500, 20, list(range(24)) + list(range(24 * 7, 24 * 8))
+    dtype = np.float64
+    threads = 16
+    data = Model.syn_gen(m, n, k, lag_set, seed=0, dtype=dtype)
+    data["Y"] += 10
+    m0 = Model.initialize(data["Y"], data["lag_set"], k + 20, seed=0)
+    print("dY={} W{} H{}".format(norm(data["Y"] - m0.W.dot(m0.H.T)), norm(m0.W), norm(m0.H)))
+    train(data["Y"], m0, lambdaI=0.01, lambdaAR=0.001, lambdaLag=0.0001, max_iter=20, missing=missing, verbose=1, threads=threads)
+    print("dY={} W{} H{}".format(norm(data["Y"] - m0.W.dot(m0.H.T)), norm(m0.W), norm(m0.H)))
+    print(rolling_validate(data["Y"], data["lag_set"], k, 24, 7, lambdaI=0.001, lambdaAR=0.001, lambdaLag=0.2, threshold=None))
