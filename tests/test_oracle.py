@@ -75,3 +75,16 @@ def test_numpy_oracle_matches_live_reference(missing):
     Wn, Hn, Ln = tn.train(Y, p["lags"], p["W0"], p["H0"], p["L0"], trace=trace, **kw)
     assert cases.rel(Wn, Wr) < TOL and cases.rel(Hn, Hr) < TOL and cases.rel(Ln, Lr) < TOL
     assert all(t["accepted"] for t in trace) and all(1 <= t["cg_iter"] <= 20 for t in trace)
+
+
+@pytest.mark.skipif(not abi.ref_available(np.float64), reason="oracle/_ref not built (make -C oracle)")
+@pytest.mark.parametrize("missing", [True, False])
+def test_lag_zero_is_a_legal_lag(missing):
+    """The reference's own smoke run uses lag_set = range(24) + range(168, 192), i.e. lag 0 (trmf.py:353): the
+    restatement follows the reference there too."""
+    p = cases.make_problem(90, 40, 5, [0, 1, 2, 7], 0.7, seed=3)
+    Y = p["Ysp"] if missing else p["Y"]
+    kw = dict(lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=2, period_Lag=1, missing=missing)
+    Wr, Hr, Lr = abi.run_reference(Y, p["lags"], p["W0"], p["H0"], p["L0"], threads=2, **kw)
+    Wn, Hn, Ln = tn.train(Y, p["lags"], p["W0"], p["H0"], p["L0"], **kw)
+    assert cases.rel(Wn, Wr) < TOL and cases.rel(Hn, Hr) < TOL and cases.rel(Ln, Lr) < TOL

@@ -306,6 +306,23 @@ def test_mma_gram_kernel_every_rank_ragged_and_badly_scaled(k, monkeypatch):
     s.close()
 
 
+@pytest.mark.parametrize("dtype,tol", [(np.float64, 10 * TOL64)])
+@pytest.mark.parametrize("missing", [True, False])
+def test_lag_zero_is_a_legal_lag(dtype, tol, missing):
+    """lag_set may contain 0 -- the reference's own smoke run does (trmf.py:353); oracle pinned on it in
+    tests/test_oracle.py::test_lag_zero_is_a_legal_lag.  Two outer iterations, float64 library."""
+    p = cases.make_problem(90, 40, 8, [0, 1, 2, 7], 0.7, seed=3)
+    f = lambda a: np.asarray(a, dtype=dtype)
+    Ysp = sps.csr_matrix((f(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    Y = Ysp if missing else f(p["Y"])
+    W0, H0, L0 = f(p["W0"]), f(p["H0"]), f(p["L0"])
+    kw = dict(lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=2, period_Lag=1, missing=missing)
+    W, H, L = run_cuda(Y, p["lags"], W0, H0, L0, dtype, **kw)
+    Wo, Ho, Lo = tn.train(Y.astype(np.float64), p["lags"], W0.astype(np.float64), H0.astype(np.float64),
+                          L0.astype(np.float64), **kw)
+    assert max(cases.rel(W, Wo), cases.rel(H, Ho), cases.rel(L, Lo)) < tol
+
+
 @pytest.mark.parametrize("dtype,mode,k", [(np.float32, "sparse", 40), (np.float32, "sparse", 8), (np.float32, "dense", 20),
                                           (np.float64, "dense", 20), (np.float64, "sparse", 8), (np.float32, "dense_sparse_storage", 8)])
 @pytest.mark.parametrize("lam_ar", [0.5, 500.0])
