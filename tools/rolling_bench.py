@@ -10,6 +10,10 @@ Workloads (the real datasets are not obtainable offline): "electricit
 "traffic" = configs[2] shape (T = 10 560, n = 963, k = 40, lags 1..24,168,336) run sparse (10 % exact zeros,
 missing=True); "c2" = configs[1] shape (T = n = 10 000, k = 40, lags {1,7,24}, 10 % zeros, missing=True).
 Wall-clock of the whole call (host work included: this is a host-level API); one JSON line per config.
+
+`oracle/` appears here in exactly the role it has in bench.py's `cpu_baseline` leg: the compiled reference
+(`oracle/_ref`, driven through `oracle.abi`) is TIMED next to the product as the CPU baseline (`--no-reference` skips
+it); the two measured product paths never touch it.
 """
 import argparse
 import json
