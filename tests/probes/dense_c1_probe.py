@@ -2,7 +2,7 @@
 trmf.train on the GPU next to the compiled reference on the host cores; prints times and parity."""
 import os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "exp-trmf-nips16_b200")); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import trmf
 from oracle import abi

@@ -1,3 +1,5 @@
+"""Accuracy probe (checker, hence under tests/): float32 CUDA library against the NumPy float64 oracle after 1-3 outer
+iterations at a few medium shapes; prints relative Frobenius errors.  Run on the GPU box: python tests/probes/errprobe.py"""
 import os, sys, numpy as np, scipy.sparse as sps
 sys.path.insert(0,'/root/repo'); sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo/exp-trmf-nips16_b200')
 import cases
