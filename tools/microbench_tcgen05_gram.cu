@@ -95,7 +95,8 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(UN 
 //   mode 0: convert + MMA;  mode 1: MMAs only, re-using the first NST converted tiles (issue floor).
 // out: 128 x 48 floats (D, summed over flushes); cyc: clock64 ticks of the main loop.
 __global__ void __launch_bounds__(128, 1)
-gram_tc_kernel(const float *__restrict__ X, int ntiles, int flush_tiles, int mode, float *__restrict__ out, long long *__restrict__ cyc) {
+gram_tc_kernel(const float *__restrict__ X, int ntiles, int flush_tiles, int mode, float *__restrict__ out, long long *__restrict__ cyc,
+               uint32_t lbo_bytes, uint32_t sbo_bytes) {
     extern __shared__ __align__(1024) unsigned char smem[];
     __shared__ __align__(8) unsigned long long bars[NST + 1];
     __shared__ uint32_t tmem_base_s;
@@ -167,8 +168,8 @@ gram_tc_kernel(const float *__restrict__ X, int ntiles, int flush_tiles, int mod
         if (tid == 0) {
             tc_fence_after();
             const uint32_t a_addr = smem_u32(tile);
-            const uint64_t da = make_desc(a_addr, 128, GROUP_BYTES);   // A: 16 groups (128 rows) x 16 entries
-            const uint64_t db = make_desc(a_addr, 128, GROUP_BYTES);   // B: the first 6 groups of the same tile (h1, N = 48)
+            const uint64_t da = make_desc(a_addr, lbo_bytes, sbo_bytes);   // A: 16 groups (128 rows) x 16 entries
+            const uint64_t db = make_desc(a_addr, lbo_bytes, sbo_bytes);   // B: the first 6 groups of the same tile (h1, N = 48)
             umma_f16(tmem_d, da, db, IDESC, since_flush > 0 ? 1u : 0u);
             if (mode == 0) umma_commit(smem_u32(&bars[s]));
         }
@@ -218,6 +219,19 @@ int main() {
     CHECK(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     std::vector<float> D((size_t)UM * UN);
     long long cyc = 0;
+    // (a0) which descriptor field carries which stride?  Reading of cute::make_umma_desc<Major::MN> for SWIZZLE_NONE:
+    // LBO = distance between the two 8-entry K groups (128 B), SBO = distance between 8-column MN groups (256 B).
+    // Try that and the swapped assignment; continue with whichever reproduces the fp64 Gram.
+    uint32_t lbo = 128, sbo = GROUP_BYTES;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const uint32_t l = attempt == 0 ? 128u : (uint32_t)GROUP_BYTES, sb = attempt == 0 ? (uint32_t)GROUP_BYTES : 128u;
+        gram_tc_kernel<<<1, 128, smem>>>(dX, 1, 0, 0, dD, dC, l, sb);
+        CHECK(cudaDeviceSynchronize());
+        CHECK(cudaMemcpy(D.data(), dD, D.size() * sizeof(float), cudaMemcpyDeviceToHost));
+        const double err = check(X, ET, D.data());
+        printf("(a0) descriptor LBO = %u B, SBO = %u B: one tile, rel. error %.2e%s\n", l, sb, err, err < 1e-3 ? "  <- correct" : "");
+        if (err < 1e-3) { lbo = l; sbo = sb; break; }
+    }
     printf("(a)/(b) accuracy of G = D_top + S + S' against fp64, one CTA, by entries accumulated in TMEM between flushes\n");
     const int tiles_list[] = {1, 8, 64, 512};
     const int flush_list[] = {0, 1, 8, 32};
@@ -225,7 +239,7 @@ int main() {
         for (int fl : flush_list) {
             if (fl >= nt && fl != 0) continue;
             // one CTA reads the first nt tiles of its slice; slice stride = nt tiles, so CTA 0 sees X[0 .. nt*16)
-            gram_tc_kernel<<<1, 128, smem>>>(dX, nt, fl, 0, dD, dC);
+            gram_tc_kernel<<<1, 128, smem>>>(dX, nt, fl, 0, dD, dC, lbo, sbo);
             CHECK(cudaDeviceSynchronize());
             CHECK(cudaMemcpy(D.data(), dD, D.size() * sizeof(float), cudaMemcpyDeviceToHost));
             CHECK(cudaMemcpy(&cyc, dC, sizeof cyc, cudaMemcpyDeviceToHost));
@@ -234,7 +248,7 @@ int main() {
         }
     printf("(c) all %d SMs, %d tiles each\n", sms, max_tiles);
     for (int mode = 0; mode < 2; ++mode) {
-        gram_tc_kernel<<<sms, 128, smem>>>(dX, max_tiles, 8, mode, dD, dC);
+        gram_tc_kernel<<<sms, 128, smem>>>(dX, max_tiles, 8, mode, dD, dC, lbo, sbo);
         CHECK(cudaDeviceSynchronize());
         std::vector<long long> c(sms);
         CHECK(cudaMemcpy(c.data(), dC, sms * sizeof(long long), cudaMemcpyDeviceToHost));
