@@ -32,6 +32,8 @@ python tools/ncu_summary.py "$out/launches_c2.csv" > "$out/launches_c2.txt"; hea
 if [ "$mode" = "full" ]; then
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench_tcgen05_gram tools/microbench_tcgen05_gram.cu && \
         timeout 120 tools/microbench_tcgen05_gram > "$out/microbench_tcgen05_gram.txt" 2>&1; cat "$out/microbench_tcgen05_gram.txt"
+    nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/proto_f_update_tc tools/proto_f_update_tc.cu && \
+        timeout 120 tools/proto_f_update_tc > "$out/proto_f_update_tc.txt" 2>&1; cat "$out/proto_f_update_tc.txt"
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/microbench_cg tools/microbench_cg.cu && \
         timeout 120 tools/microbench_cg > "$out/microbench_cg.txt" 2>&1; cat "$out/microbench_cg.txt"
     timeout 400 ncu --set full --clock-control none --import-source on -k regex:f_update_mma -c 4 -o "$out/f_update_mma_full" -f \
