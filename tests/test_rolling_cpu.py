@@ -206,3 +206,39 @@ def test_rolling_loop_matches_the_reference_core(monkeypatch, name, resident):
                                 _models_out=models, **kw)
     check_models_against_golden(g, name, models, 1e-9)
     assert np.allclose(np.array(list(met)), g[name + "_metrics"], rtol=1e-9, atol=0)
+
+
+# ---- property test: any shape / window plan / option mix, resident host logic == the reference's per-window loop ----
+try:
+    from hypothesis import given, settings, strategies as st, HealthCheck
+    HAVE_HYPOTHESIS = True
+except Exception:       # pragma: no cover
+    HAVE_HYPOTHESIS = False
+
+if HAVE_HYPOTHESIS:
+    @settings(max_examples=25, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(n=st.integers(1, 6), k=st.integers(1, 4), window_size=st.integers(1, 5), nr_windows=st.integers(1, 4),
+           lag_pool=st.lists(st.integers(0, 9), min_size=1, max_size=4, unique=True), missing=st.booleans(),
+           transform=st.sampled_from([None, True]), max_iter=st.integers(1, 3), seed=st.integers(0, 5),
+           f32=st.booleans())
+    def test_resident_rolling_property(monkeypatch, n, k, window_size, nr_windows, lag_pool, missing, transform, max_iter, seed, f32):
+        from hypothesis import assume
+        assume(nr_windows * window_size >= 2)      # Metrics' MASE needs two rows of truth (reference trmf.py:290-294 too)
+        T = max(lag_pool) + 12 + nr_windows * window_size
+        Y = series(T, n, seed=seed, zeros=missing)
+        if f32:
+            Y = Y.astype(np.float32)
+        if missing:
+            Y[0, :] = 1.0          # keep every series observed at least once in every window
+        monkeypatch.setattr(tmod, "train", oracle_train)
+        monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+        kw = dict(k=k, window_size=window_size, nr_windows=nr_windows, lambdaI=0.5, lambdaAR=5.0, lambdaLag=0.5, max_iter=max_iter,
+                  missing=missing, transform=transform, seed=seed)
+        m_host, m_res = [], []
+        with np.errstate(all="ignore"):
+            host = trmf.rolling_validate(Y, lag_pool, resident=False, _models_out=m_host, **kw)
+            res = trmf.rolling_validate(Y, lag_pool, resident=True, _models_out=m_res, **kw)
+        assert len(m_host) == len(m_res) == nr_windows
+        for a, b in zip(m_host, m_res):
+            assert np.array_equal(a.W, b.W) and np.array_equal(a.H, b.H) and np.array_equal(a.lag_val, b.lag_val)
+        assert np.array_equal(np.array(list(host)), np.array(list(res)), equal_nan=True)
