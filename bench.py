@@ -23,6 +23,11 @@ import argparse
 import ctypes
 import json
 import os
+
+# The reference calls BLAS ?dot once per observed entry from inside its OpenMP team (trmf.cpp:238): a threaded
+# OpenBLAS oversubscribes the cores and handicaps the CPU arm ~2x (round-1 VERDICT).  One BLAS thread, set before
+# NumPy (whose bundled OpenBLAS oracle/_ref links) is imported; cpu legs also pin it through threadpoolctl.
+os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
 import subprocess
 import sys
 import tempfile
@@ -49,7 +54,12 @@ CONFIGS = {
 }
 LAMBDAS = (0.5, 50.0, 0.5)   # rolling_validate defaults, reference trmf.py:303
 RANK_TRUE, NOISE, SEED = 8, 0.01, 20161205
-SAMPLE_SERIES = 2500          # CPU arms: first 2500 series of the workload (all T time stamps)
+# CPU arms run the WHOLE workload when it has at most this many observed entries (C2 at N = 1: 9.0e7, ~5 s per outer
+# iteration on 16 cores); larger ones (C4, C5, weak-scaled C2 at N > 1) are timed on the first SAMPLE_SERIES series
+# and labelled as a sample -- entries/s is an intensive quantity of this solver (cost per entry does not depend on n).
+FULL_CPU_NNZ = 1.3e8
+SAMPLE_SERIES = 10000
+PARITY_SERIES = 10000         # parity problem: the first min(n, 10000) series' worth of the workload, sharded over all ranks
 
 # --------------------------------------------------------------------------
 # host twin of csrc/synth.cuh (bit-identical; verified by tests/test_synth_gpu.py)
@@ -84,19 +94,23 @@ def host_synth(T, n, n_total, col_offset, r, p, noise, seed, dtype, row_block=51
         Wn = _normal(_key(seed, 1, (np.arange(T, dtype=np.uint64)[:, None] * np.uint64(64) + np.arange(r, dtype=np.uint64)[None, :])))
         jg = np.arange(col_offset, col_offset + n, dtype=np.uint64)
         Hn = _normal(_key(seed, 2, jg[:, None] * np.uint64(64) + np.arange(r, dtype=np.uint64)[None, :]))
-        rows, cols, vals = [], [], []
-        for i0 in range(0, T, row_block):
-            i1 = min(T, i0 + row_block)
-            cell = np.arange(i0, i1, dtype=np.uint64)[:, None] * np.uint64(n_total) + jg[None, :]
-            obs = (_key(seed, 4, cell) >> np.uint64(40)).astype(np.uint32) < thresh
-            ii, jj = np.nonzero(obs)
-            acc = np.zeros(len(ii))
-            for q in range(r):
-                acc = acc + Wn[i0 + ii, q] * Hn[jj, q]
-            z = _normal(_key(seed, 3, cell[ii, jj]))
-            acc = acc + noise * z
-            rows.append((ii + i0).astype(np.int32)); cols.append(jj.astype(np.int32)); vals.append(acc.astype(dtype))
-        rows, cols, vals = np.concatenate(rows), np.concatenate(cols), np.concatenate(vals)
+        def block(i0):
+            with np.errstate(over="ignore"):
+                i1 = min(T, i0 + row_block)
+                cell = np.arange(i0, i1, dtype=np.uint64)[:, None] * np.uint64(n_total) + jg[None, :]
+                obs = (_key(seed, 4, cell) >> np.uint64(40)).astype(np.uint32) < thresh
+                ii, jj = np.nonzero(obs)
+                acc = np.zeros(len(ii))
+                for q in range(r):
+                    acc = acc + Wn[i0 + ii, q] * Hn[jj, q]
+                z = _normal(_key(seed, 3, cell[ii, jj]))
+                acc = acc + noise * z
+                return (ii + i0).astype(np.int32), jj.astype(np.int32), acc.astype(dtype)
+        from concurrent.futures import ThreadPoolExecutor
+        row_block = max(16, min(row_block, (1 << 22) // max(n, 1)))     # ~4M cells per block
+        with ThreadPoolExecutor(max_workers=max(1, min(16, os.cpu_count() or 1))) as ex:   # NumPy releases the GIL
+            parts = list(ex.map(block, range(0, T, row_block)))
+        rows, cols, vals = (np.concatenate([q[c] for q in parts]) for c in range(3))
     csr = sps.csr_matrix((vals, (rows, cols)), shape=(T, n))
     csr.sort_indices()
     csc = csr.tocsc()
@@ -226,44 +240,132 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(k):
-    """dram bytes per F-kernel launch from the committed ncu --set full capture, if any."""
+def ncu_traffic(config, k, world, kernel="f_update"):
+    """dram bytes per launch of `kernel` from the committed ncu --set full captures (profiles/kernel_traffic.json,
+    keyed "<kernel>:<config>:k<k>:n<gpus>"), or None when no capture matches this workload."""
     try:
-        with open(os.path.join(ROOT, "profiles", "f_update_traffic.json")) as fh:
+        with open(os.path.join(ROOT, "profiles", "kernel_traffic.json")) as fh:
             d = json.load(fh)
-        return d.get("dram_bytes_per_launch")
+        e = d.get("{}:{}:k{}:n{}".format(kernel, config, k, world))
+        return None if e is None else e.get("dram_bytes_per_launch")
     except Exception:
         return None
 
 
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except Exception:
+        pass
+    return set()
+
+
 def ref_lib(dtype):
+    """oracle/_ref library for this host: the AVX-512 build (-march=x86-64-v4) when the CPU has it, else the
+    -march=x86-64-v3 one.  (The reference's own flag is -march=native, corelib/Makefile:2; its sources do not travel to
+    the GPU box, so the library is built in the CPU container for the two ISA levels instead.)"""
     from oracle import abi
     p = abi.ref_lib_path(dtype)
-    return p if os.path.exists(p) else None
+    v4 = p.replace(".so", "_v4.so")
+    if os.path.exists(v4) and {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"} <= _cpu_flags():
+        return v4, "x86-64-v4"
+    return (p, "x86-64-v3") if os.path.exists(p) else (None, None)
 
 
-def cpu_one_iteration(csr, lags, W0, H0, L0, dtype, threads):
-    """One outer iteration on the host: the compiled reference (kind 'reference') or,
-    if oracle/_ref did not travel, the NumPy oracle (kind 'port')."""
+def _blas_single_thread():
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1, user_api="blas")
+    except Exception:
+        import contextlib
+        return contextlib.nullcontext()
+
+
+def _capture_fds(fn):
+    """Run fn() with the C-level stdout/stderr redirected to a temp file; returns (result, text)."""
+    libc = ctypes.CDLL(None)
+    sys.stdout.flush(); sys.stderr.flush(); libc.fflush(None)
+    saved = os.dup(1), os.dup(2)
+    with tempfile.TemporaryFile() as tmp:
+        os.dup2(tmp.fileno(), 1); os.dup2(tmp.fileno(), 2)
+        try:
+            out = fn()
+        finally:
+            libc.fflush(None)
+            os.dup2(saved[0], 1); os.dup2(saved[1], 2)
+            os.close(saved[0]); os.close(saved[1])
+        tmp.seek(0)
+        return out, tmp.read().decode(errors="replace")
+
+
+def cpu_one_iteration(hY, lags, W0, H0, L0, dtype, threads, trace=False):
+    """One outer iteration F -> X -> lag_val on the host cores: the compiled reference (kind 'reference') or, if
+    oracle/_ref did not travel, the NumPy oracle (kind 'port').  hY: oracle.abi.HostMatrix (reference) / scipy CSR.
+    trace=True also returns the CG step count parsed from the reference's verbose=2 TRON line (rf_tron.h:219)."""
     from oracle import abi, trmf_numpy as tn
     kw = dict(lambdaI=LAMBDAS[0], lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2], max_iter=1, period_W=1, period_H=1,
               period_Lag=1, missing=True)
-    lib = ref_lib(dtype)
+    lib, march = ref_lib(dtype)
     if lib is not None:
-        hY = abi.HostMatrix(csr, dtype)
-        t0 = time.perf_counter()
-        out = abi.run_train(lib, hY, lags, W0, H0, L0, dtype=dtype, threads=threads, **kw)
-        return time.perf_counter() - t0, "reference", threads, out
+        with _blas_single_thread():
+            t0 = time.perf_counter()
+            if trace:
+                out, text = _capture_fds(lambda: abi.run_train(lib, hY, lags, W0, H0, L0, dtype=dtype, threads=threads, verbose=2, **kw))
+            else:
+                out, text = abi.run_train(lib, hY, lags, W0, H0, L0, dtype=dtype, threads=threads, **kw), ""
+            dt = time.perf_counter() - t0
+        cg = None
+        for line in text.splitlines():
+            f = line.split()
+            if "CG" in f and line.lstrip().startswith("iter"):
+                cg = int(f[f.index("CG") + 1])
+        return dt, "reference", threads, out, cg, march
     t0 = time.perf_counter()
-    out = tn.train(csr.astype(np.float64), lags, W0, H0, L0, **kw)
-    return time.perf_counter() - t0, "port", 1, out
+    tr = []
+    out = tn.train((hY.astype(np.float64) if hasattr(hY, "astype") else hY), lags, W0, H0, L0, trace=tr, **kw)
+    cg = None
+    for e in tr:
+        if isinstance(e, dict) and "cg_iter" in e:
+            cg = int(e["cg_iter"])
+    return time.perf_counter() - t0, "port", 1, out, cg, "numpy"
 
 
-def sample_problem(cfg, dtype, n_total):
-    ns = min(SAMPLE_SERIES, cfg["n"])
+def cpu_problem(cfg, dtype, n_total, full_ok=True):
+    """Host twin of the workload for the CPU legs: all of it when small enough, else its first SAMPLE_SERIES series."""
+    est_nnz = cfg["T"] * n_total * cfg["p"]
+    ns = n_total if (full_ok and est_nnz <= FULL_CPU_NNZ) else min(SAMPLE_SERIES, n_total)
     csr, _ = host_synth(cfg["T"], ns, n_total, 0, RANK_TRUE, cfg["p"], NOISE, SEED, dtype)
     W0, H0, L0 = init_factors(cfg["T"], n_total, cfg["k"], len(cfg["lags"]), dtype)
-    return csr, W0, H0[:ns].copy(), L0, ns
+    if ns == n_total:
+        what = "the whole workload ({} series x T={} time stamps, nnz={})".format(ns, cfg["T"], csr.nnz)
+    else:
+        what = "sample: first {} of {} series, all T={} time stamps, nnz={} (entries/s does not depend on n)".format(
+            ns, n_total, cfg["T"], csr.nnz)
+    return csr, W0, H0[:ns].copy(), L0, ns, what
+
+
+def cpu_baseline_leg(cfg, dtype, n_total, steps=1, warmup=0):
+    """Times the reference's own OpenMP solver on the box's host cores; returns (dict, host problem)."""
+    from oracle import abi
+    threads = os.cpu_count() or 1
+    csr, W0, H0, L0, ns, what = cpu_problem(cfg, dtype, n_total)
+    lags = np.array(cfg["lags"], dtype=np.uint32)
+    lib, _ = ref_lib(dtype)
+    hY = abi.HostMatrix(csr, dtype) if lib is not None else csr
+    times, kind, cores, march = [], None, 1, None
+    for it in range(warmup + steps):
+        dt, kind, cores, _, _, march = cpu_one_iteration(hY, lags, W0, H0, L0, dtype, threads)
+        if it >= warmup:
+            times.append(dt)
+    sec = float(np.mean(times))
+    d = {"value": csr.nnz / sec, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": sec,
+         "sample": what + "; one outer iteration F->X->lag_val from the bench's initial factors",
+         "same_config": ns == n_total, "blas_threads": 1, "march": march,
+         "note": "compiled reference core (oracle/_ref), OpenMP threads = host cores, OPENBLAS_NUM_THREADS=1"}
+    return d, (csr, W0, H0, L0, ns)
 
 
 # --------------------------------------------------------------------------
@@ -274,23 +376,14 @@ def run_reference_arm(args, cfg, rank, world):
         return
     dtype = np.float32
     n_total = cfg["n"] * (world if cfg["weak"] else 1)
-    threads = os.cpu_count() or 1
-    csr, W0, H0, L0, ns = sample_problem(cfg, dtype, n_total)
-    lags = np.array(cfg["lags"], dtype=np.uint32)
-    times, kind, cores = [], None, 1
-    for it in range(args.warmup + args.steps):
-        dt, kind, cores, _ = cpu_one_iteration(csr, lags, W0, H0, L0, dtype, threads)
-        if it >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * float(np.mean(times))
-    value = csr.nnz / (ms * 1e-3)
-    sample = "first {} of {} series, all T={} time stamps, nnz={}; one outer iteration F->X->lag from the bench's initial factors".format(
-        ns, n_total, cfg["T"], csr.nnz)
+    cb, _ = cpu_baseline_leg(cfg, dtype, n_total, steps=args.steps, warmup=args.warmup)
+    value, ms = cb["value"], 1e3 * cb["seconds"]
     line = {"impl": "reference", "metric": "observed entries/sec per ALS outer iter", "value": value, "unit": "entries/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak" if cfg["weak"] else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": cfg["name"], "T": cfg["T"], "n": n_total, "k": cfg["k"], "sample": sample},
-            "cpu_baseline": {"value": value, "unit": "entries/s", "cores": cores, "kind": kind, "sample": sample},
+            "config": {"workload": cfg["name"], "T": cfg["T"], "n": n_total, "k": cfg["k"], "lag_set": cfg["lags"],
+                       "lambdas": LAMBDAS, "sample": cb["sample"], "same_config": cb["same_config"]},
+            "cpu_baseline": cb,
             "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -298,7 +391,8 @@ def run_reference_arm(args, cfg, rank, world):
 # --------------------------------------------------------------------------
 # B200 arm
 # --------------------------------------------------------------------------
-def run_b200_arm(args, cfg, rank, world, local_rank):
+def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
+    """light=True: the strong-scaling side record (few steps, no e2e / parity / clock sampling)."""
     import torch
     import torch.distributed as dist
     from trmf.rf_util import PyMatrix
@@ -365,21 +459,21 @@ def run_b200_arm(args, cfg, rank, world, local_rank):
     except Exception:
         bus_id = None
     sampler = ClockSampler(local_rank, bus_id)
-    if rank == 0:
+    if rank == 0 and not light:
         sampler.start()
     launches0 = s.stat("kernel_launches")
     coll0 = s.stat("collectives")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fk_ms, f_ms, x_ms, lag_ms, cg = [], [], [], [], []
+    fk_ms, f_ms, x_ms, lag_ms, cg, xg_ms = [], [], [], [], [], []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             step()
             fk_ms.append(s.stat("f_kernel_ms")); f_ms.append(s.stat("f_ms")); x_ms.append(s.stat("x_ms"))
-            lag_ms.append(s.stat("lag_ms")); cg.append(int(s.stat("cg_iters")))
+            lag_ms.append(s.stat("lag_ms")); cg.append(int(s.stat("cg_iters"))); xg_ms.append(s.stat("x_gram_ms"))
         e1.record(stream)
     barrier()
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop() if (rank == 0 and not light) else None
     total_ms = e0.elapsed_time(e1)
     launches = int(s.stat("kernel_launches") - launches0)
     collectives = int(s.stat("collectives") - coll0)
@@ -399,13 +493,30 @@ def run_b200_arm(args, cfg, rank, world, local_rank):
     achieved = bytes_f / (fk * 1e-3) / 1e9
     flops_f = nnz_loc * (k * k + 3 * k) + n_loc * (k ** 3 / 3 + 2 * k * k)
     roofline = {"bound": "hbm", "kernel": "f_update (Gram + Cholesky per series)", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(k), "peak_source": peak_src,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(cfg_key, k, world), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_f, "kernel_ms": fk, "fp32_tflops": flops_f / (fk * 1e-3) / 1e12,
                 "entries_per_s": nnz_loc / (fk * 1e-3)}
+    # ---- second roofline: the X-update's Gram build with the fused loss value / gradient (rows = time stamps).
+    # Algorithmic bytes: the same gather model, N(8+4k) + T(8+4k), plus the T k^2 fp32 Grams it stores.
+    xg = float(np.mean(xg_ms)) if xg_ms and np.mean(xg_ms) > 0 else None
+    roofline_x = None
+    if xg:
+        bytes_x = nnz_loc * (8 + 4 * k) + T * (8 + 4 * k) + T * k * k * 4
+        roofline_x = {"bound": "hbm", "kernel": "x_update Gram build + fused fun/grad (per time stamp)", "achieved": bytes_x / (xg * 1e-3) / 1e9,
+                      "peak": peak, "unit": "GB/s", "frac": bytes_x / (xg * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(cfg_key, k, world, "x_gram"),
+                      "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_x, "kernel_ms": xg,
+                      "entries_per_s": nnz_loc / (xg * 1e-3)}
 
     # ---- end to end through the public host-buffer API ----
-    e2e = None if args.no_e2e else run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0,
-                                           n_loc, nnz_loc, nnz_total)
+    e2e = None if (args.no_e2e or light) else run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0,
+                                                      n_loc, nnz_loc, nnz_total)
+    # ---- parity of this build against the float64 reference (driver-visible, every N) ----
+    parity = None
+    if not (light or args.no_parity):
+        try:
+            parity = parity_block(cfg, torch, dist, lib, s, dtype, rank, world, local_rank)
+        except Exception as e:   # never lose the bench line over the checker
+            parity = {"error": "{}: {}".format(type(e).__name__, e)}
 
     s.close()
     lib.trmf_b200_free_synth(ctypes.byref(sd))
@@ -420,9 +531,92 @@ def run_b200_arm(args, cfg, rank, world, local_rank):
                            "l2": "inputs larger than L2 (Y = {:.2f} GB per GPU in two orientations); no flush".format(nnz_loc * 16 / 1e9),
                            "step": "one outer iteration F->X->lag_val restarted from the same factors"},
                 "e2e": e2e, "gpu_launches": launches, "collectives": collectives, "clocks": clocks, "roofline": roofline,
+                "roofline_x": roofline_x, "parity": parity,
                 "phase_ms": {"f_update": float(np.mean(f_ms)), "x_update": float(np.mean(x_ms)), "lag_update": float(np.mean(lag_ms))},
                 "cg_steps": cg}
     return line
+
+
+def parity_block(cfg, torch, dist, lib, s_owner, dtype, rank, world, local_rank):
+    """fp32 CUDA path against the FLOAT64 build of the compiled reference: one outer iteration F -> X -> lag_val from
+    identical factors on the parity problem = min(n, PARITY_SERIES) series of the workload's generator (at N = 1 and
+    the default config: the bench workload itself), sharded over all ranks exactly like the timed run.  Relative
+    Frobenius distance of W, H, lag_val (north_star bar: 1e-5) and equality of the CG step counts."""
+    from trmf.session import Session, SynthDesc
+    T, k, lags = cfg["T"], cfg["k"], np.array(cfg["lags"], dtype=np.uint32)
+    n_p = min(PARITY_SERIES, cfg["n"])
+    bounds = [n_p * r // world for r in range(world + 1)]
+    col0, n_loc = bounds[rank], bounds[rank + 1] - bounds[rank]
+    dev = torch.device("cuda", local_rank)
+    sd = SynthDesc()
+    if lib.trmf_b200_synth_generate(ctypes.byref(sd), T, n_loc, n_p, col0, RANK_TRUE, cfg["p"], NOISE, SEED, local_rank) != 0:
+        raise RuntimeError("synth_generate failed: " + lib.trmf_b200_last_error().decode())
+    W0, H0, L0 = init_factors(T, n_p, k, len(lags), dtype)
+    dW, dH, dL = (torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in (W0, H0[col0:col0 + n_loc], np.ascontiguousarray(L0.T)))
+    sp = Session.from_device(dtype, T, n_loc, int(sd.nnz), k, sd.d_row_ptr, sd.d_col_idx, sd.d_val_t, sd.d_col_ptr,
+                             sd.d_row_idx, sd.d_val, lags, dW.data_ptr(), dH.data_ptr(), dL.data_ptr(), device=local_rank,
+                             lambdaI=LAMBDAS[0], lambdaAR=LAMBDAS[1], lambdaLag=LAMBDAS[2])
+    try:
+        if world > 1 and lib.trmf_b200_dist_attach(sp.h, s_owner.h) != 0:
+            raise RuntimeError(lib.trmf_b200_last_error().decode())
+        sp.train(max_iter=1, period_W=1, period_H=1, period_Lag=1)
+        cg_gpu, acc_gpu = int(sp.stat("cg_iters")), int(sp.stat("accepted"))
+        W, H, L = sp.download()
+    finally:
+        sp.close()
+        lib.trmf_b200_free_synth(ctypes.byref(sd))
+    if world > 1:
+        slabs = [None] * world
+        dist.all_gather_object(slabs, H)
+        H = np.concatenate(slabs, axis=0)
+    out = None
+    if rank == 0:
+        from oracle import abi
+        csr, _ = host_synth(T, n_p, n_p, 0, RANK_TRUE, cfg["p"], NOISE, SEED, dtype)
+        f64 = np.float64
+        lib64, _ = ref_lib(f64)
+        hY = abi.HostMatrix(csr.astype(f64), f64) if lib64 is not None else csr.astype(f64)
+        _, kind, _, (Wr, Hr, Lr), cg_ref, _ = cpu_one_iteration(hY, lags, W0.astype(f64), H0.astype(f64), L0.astype(f64), f64,
+                                                               os.cpu_count() or 1, trace=True)
+
+        def rel(a, b):
+            return float(np.linalg.norm(a.astype(f64) - b) / max(np.linalg.norm(b), 1e-300))
+        out = {"W": rel(W, Wr), "H": rel(H, Hr), "lag_val": rel(L, Lr), "cg_steps": cg_gpu, "cg_steps_reference": cg_ref,
+               "cg_steps_equal": (cg_ref is not None and cg_gpu == cg_ref), "accepted": acc_gpu, "tolerance": 1e-5,
+               "against": "float64 build of the {} on the fp32-rounded inputs".format(
+                   "compiled reference core (oracle/_ref)" if kind == "reference" else "NumPy restatement (oracle/trmf_numpy.py)"),
+               "problem": "T={} x n={} series (nnz={}), k={}, {} lags, sharded over {} rank(s); one outer iteration "
+                          "F->X->lag_val from the bench's initial factors".format(T, n_p, csr.nnz, k, len(lags), world)}
+        out["pass"] = bool(max(out["W"], out["H"], out["lag_val"]) <= 1e-5)
+    if world > 1:
+        dist.barrier()
+    return out
+
+
+def strong_record(args, key, rank, world, local_rank):
+    """North_star's strong-scaling target (>= 6x at 8 GPUs on the 1M x 100k synthetic): the fixed-size config `key`
+    sharded over this run's N GPUs, a few steps, next to the main (weak-scaled) line so that the driver's 1/2/4/8
+    runs carry it.  speedup_vs_n1 uses the N = 1 figure of the same code from profiles/ when present; the driver's own
+    N = 1 run of this bench supersedes it."""
+    import copy
+    a = copy.copy(args)
+    a.steps, a.warmup, a.no_e2e, a.no_parity = 3, 2, True, True
+    line = run_b200_arm(a, CONFIGS[key], rank, world, local_rank, key, light=True)
+    if rank != 0:
+        return None
+    rec = {"workload": CONFIGS[key]["name"], "scaling": "strong", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+           "ms_per_step": line["ms_per_step"], "value": line["value"], "unit": "entries/s", "nnz": line["config"]["nnz"],
+           "phase_ms": line["phase_ms"], "cg_steps": line["cg_steps"], "collectives": line["collectives"],
+           "f_update_roofline_frac": line["roofline"]["frac"]}
+    try:
+        with open(os.path.join(ROOT, "profiles", "strong_{}_n1.json".format(key))) as fh:
+            n1 = json.load(fh)
+        rec["n1_ms_per_step"] = n1["ms_per_step"]
+        rec["n1_source"] = n1.get("source", "profiles/strong_{}_n1.json".format(key))
+        rec["speedup_vs_n1"] = n1["ms_per_step"] / line["ms_per_step"]
+    except Exception:
+        rec["speedup_vs_n1"] = 1.0 if world == 1 else None
+    return rec
 
 
 def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_rank, lags, W0, H0, L0, n_loc, nnz_loc, nnz_total):
@@ -506,6 +700,9 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="skip the host-buffer arm (large configs: it pins every slab on the host)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity block (fp32 CUDA vs the float64 reference)")
+    ap.add_argument("--strong", default="c5", choices=["c5", "c4", "none"],
+                    help="fixed-size config whose strong-scaling record rides on the default (c2) line")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     rank = int(os.environ.get("RANK", "0"))
@@ -521,16 +718,20 @@ def main():
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    line = run_b200_arm(args, cfg, rank, world, local_rank)
+    line = run_b200_arm(args, cfg, rank, world, local_rank, args.config)
+    strong = None
+    if args.strong != "none" and args.config in ("c2",):
+        try:
+            strong = strong_record(args, args.strong, rank, world, local_rank)
+        except Exception as e:
+            strong = {"error": "{}: {}".format(type(e).__name__, e)}
     if rank == 0:
+        line["strong_" + args.strong if args.strong != "none" else "strong"] = strong
         if world == 1 and not args.no_cpu_baseline:
-            dtype = np.float32
-            csr, W0, H0, L0, ns = sample_problem(cfg, dtype, cfg["n"])
-            threads = os.cpu_count() or 1
-            dt, kind, cores, _ = cpu_one_iteration(csr, np.array(cfg["lags"], dtype=np.uint32), W0, H0, L0, dtype, threads)
-            line["cpu_baseline"] = {"value": csr.nnz / dt, "unit": "entries/s", "cores": cores, "kind": kind, "seconds": dt,
-                                    "sample": "first {} of {} series, all T={} time stamps, nnz={}; one outer iteration".format(
-                                        ns, cfg["n"], cfg["T"], csr.nnz)}
+            try:
+                line["cpu_baseline"], _ = cpu_baseline_leg(cfg, np.float32, cfg["n"])
+            except Exception as e:
+                line["cpu_baseline"] = {"error": "{}: {}".format(type(e).__name__, e)}
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))

@@ -150,11 +150,12 @@ struct trmf_b200_session {
 
     // stats
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
     double st_cg = 0, st_acc = 0, st_f = 0, st_fnew = 0, st_gnorm = 0, st_prered = 0, st_actred = 0;
-    double ms_f = 0, ms_x = 0, ms_lag = 0, ms_fk = 0;
+    double ms_f = 0, ms_x = 0, ms_lag = 0, ms_fk = 0, ms_xg = 0;
     unsigned long long launches = 0;
     double st_delta = 0, st_rnorm = 0;
+    bool xg_timed = false;
 };
 typedef trmf_b200_session S;
 // time stamps to size lazily allocated T-proportional buffers for (rolling sessions grow T window by window)
@@ -296,6 +297,8 @@ static int session_common_init(S *s) {
     CUDA_TRY(cudaEventCreate(&s->ev1));
     CUDA_TRY(cudaEventCreate(&s->ev2));
     CUDA_TRY(cudaEventCreate(&s->ev3));
+    CUDA_TRY(cudaEventCreate(&s->ev4));
+    CUDA_TRY(cudaEventCreate(&s->ev5));
     return 0;
 }
 
@@ -341,6 +344,8 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev2) cudaEventDestroy(s->ev2);
     if (s->ev3) cudaEventDestroy(s->ev3);
+    if (s->ev4) cudaEventDestroy(s->ev4);
+    if (s->ev5) cudaEventDestroy(s->ev5);
     if (s->stream) cudaStreamSynchronize(s->stream);   // the frees above are ordered on the stream
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -779,12 +784,43 @@ static int fun_grad_launch(S *s, const V *w, V *g) {
 // Grams (needs T*k*k values of HBM; fp32 build with a tiled-kernel-compatible k).
 static int gram_prepare(S *s) {
     if (s->gram_state != 0) return 0;
-    s->gram_state = -1;
-    if (!s->missing || f_kernel_choice(s->k, s->H) == F_KERNEL_GENERIC || getenv("TRMF_B200_NO_GRAM_HV")) return 0;
-    size_t free_b = 0, total_b = 0;
-    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    int want = 1;
+    if (!s->missing || f_kernel_choice(s->k, s->H) == F_KERNEL_GENERIC || getenv("TRMF_B200_NO_GRAM_HV")) want = 0;
     const size_t need = (Tcap(s) * (size_t)s->k * s->k + Tcap(s) * (size_t)s->k) * sizeof(V);
-    if (need > free_b / 2) return 0;
+    if (want) {
+        // memory the allocation can draw on: what the driver reports as free plus what this device's stream-ordered
+        // pool holds in reserve from earlier sessions of the process (pool_setup() never releases it)
+        size_t free_b = 0, total_b = 0;
+        CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+        cudaMemPool_t pool;
+        unsigned long long reserved = 0, used = 0;
+        if (cudaDeviceGetDefaultMemPool(&pool, s->device) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+            free_b += (size_t)(reserved - used);
+        if (need > free_b / 2) {
+            want = 0;
+            if (getenv("TRMF_B200_VERBOSE"))
+                fprintf(stderr, "[trmf-b200] note: per-time-stamp Grams (%.1f GB) do not fit (%.1f GB available): the X-update walks Omega\n",
+                        need / 1e9, free_b / 1e9);
+        }
+    }
+    if (s->world > 1) {
+        // The choice changes the sequence (count, dtype) of NCCL collectives in x_update, so it must be the same on
+        // every rank: Grams only if every rank wants them, and the kernel family must agree.
+        const int fk = f_kernel_choice(s->k, s->H);
+        double h[4] = {(double)want, (double)(fk == F_KERNEL_MMA), (double)(fk == F_KERNEL_FFMA), (double)(fk == F_KERNEL_GENERIC)};
+        CUDA_TRY(cudaMemcpyAsync(s->scal + SC_TMP, h, sizeof h, cudaMemcpyHostToDevice, s->stream));
+        if (dist_allreduce_f64(s, s->scal + SC_TMP, 4)) return 1;
+        CUDA_TRY(cudaMemcpyAsync(h, s->scal + SC_TMP, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+        CUDA_TRY(cudaStreamSynchronize(s->stream));
+        for (int q = 1; q < 4; ++q)
+            if (h[q] != 0.0 && h[q] != (double)s->world)
+                return fail("ranks disagree on the Gram kernel family (factor alignment or TRMF_B200_F_KERNEL differs between ranks)");
+        if (h[0] != (double)s->world) want = 0;
+    }
+    s->gram_state = -1;
+    if (!want) return 0;
     if (dev_alloc(&s->Gt, Tcap(s) * (size_t)s->k * s->k) || dev_alloc(&s->bt, Tcap(s) * (size_t)s->k)) return 1;
     s->gram_state = 1;
     return 0;
@@ -945,6 +981,8 @@ extern "C" int trmf_b200_x_update(S *s) {
         const bool fusable = f_kernel_choice(s->k, s->H) == F_KERNEL_MMA && !getenv("TRMF_B200_NO_FUSED_GRAD");
         s->gram_now = s->gram_state == 1 && (fusable || s->prev_cg < 0 || s->prev_cg >= 4 || getenv("TRMF_B200_FORCE_GRAM_HV"));
         bool fused = false;   // fun(w), grad(w) came out of the Gram build's own gather
+        s->xg_timed = false;
+        s->ms_xg = 0;
         if (s->gram_now) {   // Grams of the (fixed) series factor over every time stamp's observed set
             int rc;
             if (f_kernel_choice(s->k, s->H) == F_KERNEL_MMA) {
@@ -956,9 +994,12 @@ extern "C" int trmf_b200_x_update(S *s) {
                     LAUNCH(s, base_fun_kernel, ew_grid(s, tk), 256, 0, s->W, s->rho, tk, s->lambdaI, s->lambdaAR, s->part, s->ticket, s->scal + SC_FBASE);
                     LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR, (const int *)nullptr);
                     const bool one = s->world == 1;
+                    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev4, s->stream));
                     rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
                                                             one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
                                                             s->W, one ? 1 : 0, s->frow);
+                    if (s->timing) CUDA_TRY(cudaEventRecord(s->ev5, s->stream));
+                    s->xg_timed = s->timing;
                     if (!rc) {
                         LAUNCH(s, fm::sum_rows_kernel, ew_grid(s, s->T), 256, 0, s->frow, s->T, 0.5, s->part, s->ticket, s->scal + SC_FLOSS);
                         if (!one) {
@@ -1099,6 +1140,7 @@ extern "C" int trmf_b200_x_update(S *s) {
         float ms = 0;
         CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         s->ms_x = ms;
+        if (s->xg_timed) { CUDA_TRY(cudaEventElapsedTime(&ms, s->ev4, s->ev5)); s->ms_xg = ms; }
     }
     return 0;
 }
@@ -1214,6 +1256,7 @@ extern "C" double trmf_b200_stat(S *s, int32_t which) {
         case TRMF_STAT_PRERED: return s->st_prered;
         case TRMF_STAT_ACTRED: return s->st_actred;
         case TRMF_STAT_COLLECTIVES: return (double)s->collectives;
+        case TRMF_STAT_X_GRAM_MS: return s->ms_xg;
     }
     return NAN;
 }
@@ -1289,7 +1332,10 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
         for (size_t i = 0; i < pylag_val->rows * pylag_val->cols; ++i) lv[i] = (V)N(rng);
         pyW->type = TRMF_DENSE_ROWMAJOR; pyH->type = TRMF_DENSE_ROWMAJOR; pylag_val->type = TRMF_DENSE_COLMAJOR;
     }
-    if (!check_dimension(pyY, py_lag_size, pyW, pyH, pylag_val)) return;
+    if (!check_dimension(pyY, py_lag_size, pyW, pyH, pylag_val)) {
+        g_last_error = "dimension / layout check failed (see the [ERR MSG] lines on stderr); nothing was trained";
+        return;
+    }
     (void)threads;   // OpenMP thread count of the reference (trmf.cpp:636): no meaning here
     const bool trace = getenv("TRMF_B200_TRACE") != nullptr;   // host-side wall-clock split of the call, to stderr
     auto now_ms = []() {
@@ -1298,8 +1344,18 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
         return tw.tv_sec * 1e3 + tw.tv_nsec * 1e-6;
     };
     const double t0 = now_ms();
-    S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, 0);
-    if (!s) return;   // message already on stderr
+    // device: TRMF_B200_DEVICE if set, else the calling thread's current CUDA device (e.g. torch.cuda.set_device);
+    // the caller's current device is put back before returning
+    int prev_dev = 0, dev = 0;
+    const bool have_prev = cudaGetDevice(&prev_dev) == cudaSuccess;
+    if (!have_prev) cudaGetLastError();
+    dev = have_prev ? prev_dev : 0;
+    if (const char *e = getenv("TRMF_B200_DEVICE")) dev = atoi(e);
+    S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, dev);
+    if (!s) { if (have_prev) cudaSetDevice(prev_dev); return; }   // message already on stderr
+    if (verbose > 0 && s->missing && f_kernel_choice(s->k, s->W) != F_KERNEL_MMA)
+        fprintf(stderr, "[trmf-b200] note: k = %d is outside the tensor-core Gram kernels' ranks (or a factor is not 16-byte aligned): "
+                        "the slower %s kernel runs\n", s->k, f_kernel_choice(s->k, s->W) == F_KERNEL_FFMA ? "FFMA" : "generic");
     double t1 = now_ms();
     if (trace) { cudaStreamSynchronize(s->stream); t1 = now_ms(); }
     trmf_b200_set_params(s, lambdaI, lambdaAR, lambdaLag);
@@ -1311,6 +1367,7 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     std::string keep = g_last_error;
     trmf_b200_destroy(s);
     g_last_error = keep;
+    if (have_prev) cudaSetDevice(prev_dev);
     if (trace)
         fprintf(stderr, "[trmf-b200 trace] create+H2D %.2f ms, train %.2f ms, D2H %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1,
                 t3 - t2, now_ms() - t3);

@@ -383,8 +383,22 @@ def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR,
     key = (int(k), bool(missing), Y_res.shape[0], tuple(sorted(int(l) for l in lag_set)), np.dtype(Y.dtype).str)
     sess = sessions.pop(key, None) if sessions is not None else None
     if sess is None:
-        # dense in both modes: with missing=True the device keeps the non-zero cells, i.e. csr_matrix(Y_res)
-        sess = RollingSession(Y_res, lag_set, k, missing=missing, dtype=Y.dtype)
+        if sessions:
+            # a parked session under another key (other k / window_size / lag set) holds a full device copy of Y:
+            # at most one stays resident, so a grid over k or window_size cannot exhaust HBM
+            for other in list(sessions):
+                sessions.pop(other).close()
+        try:
+            # dense in both modes: with missing=True the device keeps the non-zero cells, i.e. csr_matrix(Y_res)
+            sess = RollingSession(Y_res, lag_set, k, missing=missing, dtype=Y.dtype)
+        except RuntimeError as e:
+            if "out of memory" not in str(e).lower():
+                raise
+            # Y does not fit next to what else lives on the device: the per-window path (= the reference's loop)
+            return rolling_validate(Y, lag_set, k=k, window_size=window_size, nr_windows=nr_windows, lambdaI=lambdaI,
+                                    lambdaAR=lambdaAR, lambdaLag=lambdaLag, max_iter=max_iter, missing=missing,
+                                    threshold=threshold, transform=transform, seed=seed, resident=False,
+                                    _models_out=models_out)
     sess.set_params(lambdaI, lambdaAR, lambdaLag)
     done = False
     try:
@@ -420,27 +434,39 @@ def grid_search(Y, lag_set, grid_params, pkl_file=None, **kw_args):
     """Exhaustive search over ``grid_params`` (dict name -> list of values),
     ranking by ``m_nd`` (reference trmf.py:331-346).  Every grid point is one
     ``rolling_validate``; on the resident path (its default for a dense float
-    array) the grid points share one copy of Y in HBM per (k, window_size,
-    missing) instead of re-ingesting it nr_windows times per point."""
-    results = []
-    best = Metrics.default()
+    array) consecutive grid points with the same (k, missing, resident length =
+    T - window_size, lag set, dtype) share one copy of Y in HBM instead of
+    re-ingesting it nr_windows times per point; at most one session stays parked,
+    and a session that does not fit falls back to the per-window path."""
     names = list(grid_params.keys())
+    combos = list(itertools.product(*[grid_params[name] for name in names]))
+    # Grid points that can share a resident session (same k, window_size, missing, lag set) run back to back, so that
+    # ONE device copy of Y serves all of them and only one session is alive at a time; results, the running best and
+    # its print-out are reported in the reference's order (trmf.py:336-345).
+    def share_key(combo):
+        kws = dict(kw_args)
+        kws.update(zip(names, combo))
+        return (repr(kws.get("k", 40)), repr(kws.get("window_size", 24)), repr(kws.get("missing", True)))
+    order = sorted(range(len(combos)), key=lambda i: share_key(combos[i]))   # (stable: ties keep the grid's order)
+    done = {}
     sessions = {}
     try:
-        for combo in itertools.product(*[grid_params[name] for name in names]):
+        for i in order:
             kws = dict(kw_args)
-            kws.update(zip(names, combo))
-            metrics = rolling_validate(Y, lag_set, _sessions=sessions, **kws)
-            results.append({"kws": kws, "metrics": metrics})
-            if metrics.m_nd < best.m_nd:
-                best = metrics
-                print(metrics, dict(zip(names, combo)))
+            kws.update(zip(names, combos[i]))
+            done[i] = {"kws": kws, "metrics": rolling_validate(Y, lag_set, _sessions=sessions, **kws)}
             if pkl_file is not None:
                 with open(pkl_file, "wb") as fh:
-                    pickle.dump(results, fh)
+                    pickle.dump([done[j] for j in sorted(done)], fh)
     finally:
         for sess in sessions.values():
             sess.close()
+    results = [done[i] for i in range(len(combos))]
+    best = Metrics.default()
+    for r, combo in zip(results, combos):
+        if r["metrics"].m_nd < best.m_nd:
+            best = r["metrics"]
+            print(best, dict(zip(names, combo)))
     return results, best
 
 

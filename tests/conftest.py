@@ -23,9 +23,11 @@ def _have_gpu():
         return False
 
 
-def pytest_collection_modifyitems(config, items):
-    # `-m gpu` on a box without a GPU must fail loudly, not skip: the product has no CPU path.
-    pass
+def pytest_collection_finish(session):
+    # GPU tests selected on a box without a GPU must fail loudly, not skip: the product has no CPU path.
+    if any(item.get_closest_marker("gpu") is not None for item in session.items) and not _have_gpu():
+        pytest.exit("tests marked `gpu` were selected but no CUDA device is visible: this library is GPU-only "
+                    "(run them with gpurun, or deselect with -m 'not gpu')", returncode=2)
 
 
 @pytest.fixture(scope="session")
