@@ -648,10 +648,17 @@ def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_ra
         keep.append(t)
         pm.py_buf[name] = a
         setattr(pm, name, a.ctypes.data if fields[name] is ctypes.c_void_p else a.ctypes.data_as(fields[name]))
-    # the library uploads the CSC half and derives the CSR half on the device (csrc/ingest.cuh) unless
-    # TRMF_B200_HOST_CSR is set: count the bytes that actually cross PCIe
+    # the library uploads the CSC half and derives the CSR half on the device (csrc/ingest.cuh) unless TRMF_B200_HOST_CSR is
+    # set; for a mostly-observed matrix it packs the row indices into per-series bitmaps on the host cores inside the call
+    # (csrc/trmf_b200.cu: pack_bitmap_host) unless TRMF_B200_NO_HOST_PACK is set: count the bytes that actually cross PCIe
     copied = ("col_ptr", "row_idx", "val") if not os.environ.get("TRMF_B200_HOST_CSR") else tuple(pm.py_buf)
-    h2d = sum(pm.py_buf[name].nbytes for name in copied) + W0.nbytes + H0.nbytes + L0.nbytes
+    nbytes = {name: pm.py_buf[name].nbytes for name in copied}
+    bm_bytes = n_loc * ((T + 31) // 32) * 4
+    host_pack = ("row_idx" in nbytes and not os.environ.get("TRMF_B200_HOST_CSR") and not os.environ.get("TRMF_B200_NO_HOST_PACK")
+                 and nnz_loc >= (1 << 22) and n_loc >= 16 and bm_bytes <= nnz_loc)
+    if host_pack:
+        nbytes["row_idx"] = bm_bytes
+    h2d = sum(nbytes.values()) + W0.nbytes + H0.nbytes + L0.nbytes
     d2h_bytes = W0.nbytes + H0.nbytes + L0.nbytes
     steps = max(1, min(args.steps, 9))
     times = []
@@ -688,7 +695,9 @@ def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_ra
     return {"value": nnz_total / sec, "unit": "entries/s", "ms_per_step": 1e3 * sec, "steps": steps,
             "ms_per_step_mean": 1e3 * float(np.mean(times)), "ms_per_step_min": 1e3 * float(np.min(times)), "statistic": "median",
             "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h_bytes),
-            "api": "c_trmf_train (host PyMatrix buffers, pinned; CSR half built on device)" if world == 1 else "trmf.session.Session(host slab) + NCCL"}
+            "api": "c_trmf_train (host PyMatrix buffers, pinned; CSR half built on device)" if world == 1 else "trmf.session.Session(host slab) + NCCL",
+            "ingest": ("row indices packed into per-series bitmaps by the host cores inside the call, {} B instead of {} B over PCIe".format(
+                bm_bytes, pm.py_buf["row_idx"].nbytes) if host_pack else "plain arrays")}
 
 
 def main():

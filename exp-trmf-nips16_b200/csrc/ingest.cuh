@@ -64,6 +64,41 @@ __global__ void ingest_rowptr_kernel(const uint32_t *__restrict__ keys, uint64_t
     }
 }
 
+// TRMF_SPARSE_BITMAP ingest: row_idx[col_ptr[j] ..] = the set bits of series j's bitmap (words = ceil(T / 32) per series), ascending.
+// One warp per series, 32 words per step: popc + warp prefix sum place every lane's bits.  Bit-exact by construction; a bitmap whose
+// population disagrees with col_ptr is clipped to the series' range (never writes outside it).
+__global__ void bitmap_expand_kernel(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ bitmap, uint64_t n, uint64_t T,
+                                     uint32_t words, uint32_t *__restrict__ row_idx) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
+    const uint64_t nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t j = warp; j < n; j += nwarps) {
+        uint64_t pos = col_ptr[j];
+        const uint64_t end = col_ptr[j + 1];
+        const uint32_t *bm = bitmap + j * (uint64_t)words;
+        for (uint32_t w0 = 0; w0 < words; w0 += 32) {
+            const uint32_t wi = w0 + lane;
+            uint32_t bits = wi < words ? __ldg(bm + wi) : 0u;
+            if (wi == words - 1 && (T & 31)) bits &= (1u << (T & 31)) - 1u;     // padding bits of the last word
+            const uint32_t cnt = __popc(bits);
+            uint32_t incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t up = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o) incl += up;
+            }
+            uint64_t dst = pos + (incl - cnt);
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                if (dst < end) row_idx[dst] = wi * 32u + (uint32_t)b;
+                ++dst;
+            }
+            pos += __shfl_sync(FULL_MASK, incl, 31);
+        }
+    }
+}
+
 // All arrays on the device; temporaries come from (and return to) the stream-ordered pool.  Returns a cudaError_t.
 template <typename VT>
 static cudaError_t csr_from_csc_device(cudaStream_t st, int num_sms, uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr,

@@ -202,6 +202,25 @@ __global__ void dot_kernel(const V *__restrict__ a, const V *__restrict__ b, siz
     grid_sum_commit(v, part, ticket, out, 1.0, red);
 }
 
+// Multi-GPU Hessian-vector product, epilogue of the all-reduce: acc += reduced (the sum over ranks of the per-slab partials), and,
+// in the same pass, out[slot] = <d, acc> (the d'Hd of the CG step).  Same arithmetic and summation order as axpbypcz_kernel (a = b = 1)
+// followed by dot_kernel on the same grid, so the iterates are bit-identical to the two-kernel version.
+__global__ void add_dot_kernel(V *__restrict__ acc, const V *__restrict__ reduced, const V *__restrict__ d, size_t n,
+                               double *part, unsigned *ticket, double *out, const int *gate) {
+    CG_GATE(gate);
+    __shared__ double red[32];
+    double v = 0.0;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) {
+        const V a = (V)(1.0 * (double)acc[p] + 1.0 * (double)reduced[p]);
+        acc[p] = a;
+        if (d != nullptr) v += (double)d[p] * (double)a;
+    }
+    if (out != nullptr) {
+        v = block_sum(v, red);
+        grid_sum_commit(v, part, ticket, out, 1.0, red);
+    }
+}
+
 // s = 0, r = d = -g ; rTr = <g,g>         (rf_tron.h:424-436)
 __global__ void cg_init_kernel(const V *__restrict__ g, V *__restrict__ s, V *__restrict__ r, V *__restrict__ d,
                                size_t n, double *part, unsigned *ticket, double *rtr) {

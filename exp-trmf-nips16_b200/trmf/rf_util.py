@@ -19,7 +19,7 @@ import subprocess
 import numpy as np
 import scipy.sparse as sps
 
-__all__ = ["PyMatrix", "fillprototype", "load_dynamic_library"]
+__all__ = ["PyMatrix", "fillprototype", "load_dynamic_library", "pack_bitmap"]
 
 
 def fillprototype(fn, restype, argtypes):
@@ -45,6 +45,24 @@ def load_dynamic_library(dirname, soname, forced_rebuild=False):
     return ctypes.CDLL(so)
 
 
+def pack_bitmap(col_ptr, row_idx, rows):
+    """Row indices of a CSC matrix as one bitmap per column: uint32[cols * ceil(rows / 32)], bit (i & 31) of word
+    [j][i >> 5] set iff (i, j) is stored (``TRMF_SPARSE_BITMAP`` of include/trmf_b200.h).  Indices must be sorted
+    within every column (they are, in the canonical CSC this module builds)."""
+    col_ptr = np.asarray(col_ptr).astype(np.int64)
+    row_idx = np.asarray(row_idx)
+    cols = len(col_ptr) - 1
+    words = (int(rows) + 31) // 32
+    out = np.zeros(cols * words, dtype=np.uint32)
+    if len(row_idx):
+        col_of = np.repeat(np.arange(cols, dtype=np.int64), np.diff(col_ptr))
+        widx = col_of * words + (row_idx.astype(np.int64) >> 5)
+        bit = (np.uint32(1) << (row_idx.astype(np.uint32) & np.uint32(31))).astype(np.uint64)
+        starts = np.concatenate(([0], np.flatnonzero(widx[1:] != widx[:-1]) + 1))
+        out[widx[starts]] = np.add.reduceat(bit, starts).astype(np.uint32)   # distinct bits of one word: sum == or
+    return out
+
+
 class PyMatrix(ctypes.Structure):
     """Zero-copy view descriptor handed to ``c_trmf_train``.
 
@@ -57,6 +75,7 @@ class PyMatrix(ctypes.Structure):
     DENSE_COLMAJOR = 2
     SPARSE = 3
     EYE = 4
+    SPARSE_BITMAP = 5   # additive: CSC half only, row indices as one bitmap per column (see pack_bitmap)
 
     _fields_ = [
         ("rows", ctypes.c_uint64),
@@ -71,7 +90,7 @@ class PyMatrix(ctypes.Structure):
         ("type", ctypes.c_int32),
     ]
 
-    def __init__(self, A, dtype=np.float32, major=None, twin=True, copy=True):
+    def __init__(self, A, dtype=np.float32, major=None, twin=True, copy=True, pack=False):
         """``major`` ('row' / 'col', optional, additive to the reference signature)
         settles the type tag of arrays that are both C- and F-contiguous (a
         single row or column, e.g. W with k == 1), which the reference would tag
@@ -84,6 +103,13 @@ class PyMatrix(ctypes.Structure):
         derives the missing half on the device, bit-identically
         (``csrc/ingest.cuh``).  ``trmf.train`` uses this; such a PyMatrix is not
         valid input for the reference's own core.
+
+        ``pack`` (additive, sparse only): keep the CSC half only and carry its row
+        indices as one bitmap per column (``type = SPARSE_BITMAP``): 4 bytes of
+        values + ~1/8 byte of mask per observed cell of a mostly-observed panel
+        cross PCIe instead of 8; the library expands the bitmap to the identical
+        ``row_idx`` array on the device.  Only this package's CUDA library
+        understands it.
 
         ``copy`` (additive): the reference always copies a dense array
         (``A.astype(dtype)``, rf_util.py:122).  ``copy=False`` adopts ``A`` itself
@@ -102,8 +128,8 @@ class PyMatrix(ctypes.Structure):
                 # here they are summed, which is what every caller in trmf.py relies on.
                 A = A.tocsr()
             self.type = PyMatrix.SPARSE
-            want_csr = twin or A.format != "csc"
-            want_csc = twin or A.format == "csc"
+            want_csr = (twin or A.format != "csc") and not pack
+            want_csc = twin or A.format == "csc" or pack
             if want_csr:
                 csr = sps.csr_matrix(A)
                 if not csr.has_sorted_indices:
@@ -120,6 +146,9 @@ class PyMatrix(ctypes.Structure):
                 buf["col_ptr"] = csc.indptr.astype(np.uint64)
                 buf["row_idx"] = csc.indices.astype(np.uint32)
                 buf["val"] = csc.data.astype(dtype, copy=False)
+                if pack:
+                    buf["row_idx"] = pack_bitmap(buf["col_ptr"], buf["row_idx"], self.rows)
+                    self.type = PyMatrix.SPARSE_BITMAP
         elif isinstance(A, np.ndarray):
             arr = A.astype(dtype, copy=copy)   # order='K': keeps the caller's memory layout
             if not (arr.flags.c_contiguous or arr.flags.f_contiguous):

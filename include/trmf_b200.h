@@ -36,7 +36,13 @@ enum {
     TRMF_DENSE_ROWMAJOR = 1,
     TRMF_DENSE_COLMAJOR = 2,
     TRMF_SPARSE = 3,
-    TRMF_EYE = 4
+    TRMF_EYE = 4,
+    /* additive (Y only; never produced by the reference's rf_util.py): a sparse matrix whose CSC half carries the row
+     * indices as one BITMAP per series instead of nnz uint32 indices -- `row_idx` points at cols x ceil(rows / 32) uint32
+     * words, bit (i & 31) of word [j][i >> 5] set iff entry (i, j) is observed; `col_ptr` / `val` as in TRMF_SPARSE, the
+     * CSR half absent (NULL).  A 10 %-missing panel uploads 4.1 instead of 8 bytes per observed entry; the library expands
+     * the bitmap to the identical row_idx array in HBM (csrc/ingest.cuh). */
+    TRMF_SPARSE_BITMAP = 5
 };
 
 typedef struct {
@@ -182,6 +188,11 @@ int  trmf_b200_copy_to_host(void *dst_host, const void *src_device, uint64_t byt
  * upload the caller's CSR arrays instead. */
 int  trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *row_idx,
                             const void *val, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, int32_t device);
+
+/* Ingest primitive: the row_idx array (uint32[nnz], ascending within every series) of a TRMF_SPARSE_BITMAP matrix,
+ * expanded on the device; host arrays in, host array out (parity tests of the packed ingest). */
+int  trmf_b200_bitmap_expand(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *bitmap,
+                             uint32_t *row_idx, int32_t device);
 
 /* ---- rolling-window sessions (replaces the per-window re-ingest of the reference's
  *      rolling_validate, python/trmf/trmf.py:303-329) ----

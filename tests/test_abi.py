@@ -186,3 +186,20 @@ def test_header_is_plain_c_and_pymatrix_is_80_bytes(tmp_path):
     for lib in ("trmf_float32.so", "trmf_float64.so"):
         proc = subprocess.run([str(exe), os.path.join(CORELIB, lib)], capture_output=True, text=True)
         assert proc.returncode == 0, (lib, proc.stderr)
+
+
+def test_pack_bitmap_is_the_per_series_mask():
+    """TRMF_SPARSE_BITMAP host side (trmf/rf_util.py:pack_bitmap): bit (i & 31) of word [j][i >> 5] <=> (i, j) stored."""
+    import scipy.sparse as sps
+    from trmf.rf_util import PyMatrix, pack_bitmap
+    rng = np.random.RandomState(0)
+    for T, n, d in [(300, 200, 0.7), (33, 4, 0.9), (32, 3, 1.0), (1, 1, 1.0), (64, 64, 0.0), (70001, 3, 0.5)]:
+        m = sps.random(T, n, density=d, format="csc", random_state=rng)
+        m.sort_indices()
+        bm = pack_bitmap(m.indptr, m.indices, T).reshape(n, (T + 31) // 32)
+        dense = np.zeros((n, ((T + 31) // 32) * 32), dtype=bool)
+        dense[np.repeat(np.arange(n), np.diff(m.indptr)), m.indices] = True
+        assert np.array_equal(np.packbits(dense, axis=1, bitorder="little").view(np.uint32), bm)
+    pm = PyMatrix(m, np.float32, twin=False, pack=True)
+    assert pm.type == PyMatrix.SPARSE_BITMAP == 5 and not pm.row_ptr and not pm.col_idx and not pm.val_t
+    assert len(pm.py_buf["row_idx"]) == n * ((T + 31) // 32) and pm.nnz == m.nnz

@@ -99,3 +99,94 @@ def test_slab_upload_trains_like_a_single_copy(monkeypatch):
         s.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def _naive_bitmap(csc, T):
+    words = (T + 31) // 32
+    out = np.zeros((csc.shape[1], words), dtype=np.uint32)
+    for j in range(csc.shape[1]):
+        for i in csc.indices[csc.indptr[j]:csc.indptr[j + 1]]:
+            out[j, i >> 5] |= np.uint32(1) << np.uint32(i & 31)
+    return out.ravel()
+
+
+@pytest.mark.parametrize("T,n,density", [(300, 200, 0.7), (1, 1, 1.0), (31, 5, 0.5), (32, 9, 1.0), (33, 4, 0.9), (257, 129, 0.05),
+                                         (5000, 7, 0.9), (70001, 3, 0.5), (64, 64, 0.0)])
+def test_bitmap_ingest_expands_to_the_identical_row_idx(T, n, density):
+    """TRMF_SPARSE_BITMAP (include/trmf_b200.h): one bitmap per series travels instead of nnz row indices; the device
+    expansion (csrc/ingest.cuh: bitmap_expand_kernel) must give back the canonical CSC row_idx array bit for bit."""
+    import ctypes
+    from trmf.rf_util import pack_bitmap
+    from trmf.session import _lib
+    csc = _random_csc(T, n, density, 5 + T + n, np.float32)
+    if csc.nnz > 10:
+        lil = csc.tolil()
+        lil[:, n // 2] = 0
+        csc = lil.tocsc().astype(np.float32)
+        csc.eliminate_zeros()
+        csc.sort_indices()
+    col_ptr = csc.indptr.astype(np.uint64)
+    row_idx = csc.indices.astype(np.uint32)
+    bm = pack_bitmap(col_ptr, row_idx, T)
+    if T * n <= 20000:
+        assert np.array_equal(bm, _naive_bitmap(csc, T))
+    lib = _lib(np.float32)
+    out = np.full(max(csc.nnz, 1), 0xdeadbeef, dtype=np.uint32)
+    lib.trmf_b200_bitmap_expand.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p,
+                                            ctypes.c_void_p, ctypes.c_int32]
+    assert lib.trmf_b200_bitmap_expand(T, n, csc.nnz, col_ptr.ctypes.data, bm.ctypes.data, out.ctypes.data, 0) == 0
+    assert np.array_equal(out[:csc.nnz], row_idx)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_bitmap_packed_pymatrix_trains_like_plain_indices(dtype):
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    p = cases.make_problem(250, 140, 16, [1, 3, 7], 0.8, seed=8)
+    Y = p["Ysp"].astype(dtype)
+    W0, H0, L0 = (a.astype(dtype) for a in (p["W0"], p["H0"], p["L0"]))
+    outs = []
+    for pack in (False, True):
+        pm = PyMatrix(Y.tocsc(), dtype, twin=False, pack=pack)
+        assert pm.type == (PyMatrix.SPARSE_BITMAP if pack else PyMatrix.SPARSE)
+        s = Session(pm, p["lags"], W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+        s.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
+        outs.append(s.download())
+        s.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+
+
+def test_host_packed_index_upload_trains_identically(monkeypatch):
+    """A large mostly-observed CSC given with plain row indices: the library packs them into per-series bitmaps on the
+    host cores inside the call (4.1 instead of 8 bytes per entry over PCIe) -- same arrays in HBM, same factors,
+    with the packing on (default), off, and for a caller-packed PyMatrix."""
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    dtype = np.float32
+    rng = np.random.RandomState(4)
+    T, n, k = 3001, 2300, 24
+    mask = rng.rand(T, n) < 0.7
+    mask[:, 11] = False
+    mask[:, 12] = True
+    Y = sps.csc_matrix(np.where(mask, rng.randn(T, n) + 3.0, 0.0).astype(dtype))
+    Y.sort_indices()
+    assert Y.nnz >= (1 << 22)
+    lags = np.array([1, 7, 24], dtype=np.uint32)
+    W0, H0, L0 = rng.rand(T, k).astype(dtype), rng.rand(n, k).astype(dtype), rng.randn(3, k).astype(dtype)
+    outs = []
+    for mode in ("host_pack", "plain", "caller_pack", "one_thread"):
+        monkeypatch.delenv("TRMF_B200_NO_HOST_PACK", raising=False)
+        monkeypatch.delenv("TRMF_B200_PACK_THREADS", raising=False)
+        if mode == "plain":
+            monkeypatch.setenv("TRMF_B200_NO_HOST_PACK", "1")
+        if mode == "one_thread":
+            monkeypatch.setenv("TRMF_B200_PACK_THREADS", "1")
+        pm = PyMatrix(Y, dtype, twin=False, pack=(mode == "caller_pack"))
+        s = Session(pm, lags, W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+        s.train(max_iter=1, period_W=1, period_H=1, period_Lag=1)
+        outs.append(s.download())
+        s.close()
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert np.array_equal(a, b)
