@@ -491,7 +491,8 @@ static inline int f_update_mma_solve(cudaStream_t st, int num_sms, const uint64_
         break;                                                                                                  \
     }
     switch (k) {
-        FS_CASE(8) FS_CASE(16) FS_CASE(20) FS_CASE(24) FS_CASE(32) FS_CASE(40) FS_CASE(48) FS_CASE(56) FS_CASE(60) FS_CASE(64)
+        FS_CASE(8) FS_CASE(12) FS_CASE(16) FS_CASE(20) FS_CASE(24) FS_CASE(28) FS_CASE(32) FS_CASE(36) FS_CASE(40) FS_CASE(44) FS_CASE(48) FS_CASE(52)
+        FS_CASE(56) FS_CASE(60) FS_CASE(64)
         default: return 1;
     }
 #undef FS_CASE
@@ -500,8 +501,8 @@ static inline int f_update_mma_solve(cudaStream_t st, int num_sms, const uint64_
 }
 
 static inline bool f_update_mma_supported(int k) {
-    switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: case 56: case 60: case 64: return true; }
-    return false;
+    // every multiple of 4 up to 64
+    return k >= 8 && k <= 64 && k % 4 == 0;
 }
 
 // returns 0 on success.  `wide` selects one 16-warp CTA per SM (few series: finer load balance) instead of
@@ -553,6 +554,13 @@ static inline int f_update_mma_launch(cudaStream_t st, int num_sms, const uint64
         case 64:
             if (wide) FM_LAUNCH(64, 8, 1); else FM_LAUNCH(64, 4, 2);   // (4 CTAs of 2 warps: 230 vs 214 ms at C5 -- measured, rejected)
             break;
+        // the in-between ranks (added in round 2 so that no k % 4 == 0 falls back to the FFMA / generic kernels): the narrow
+        // shape of their next larger neighbour only
+        case 12: FM_LAUNCH(12, 4, 4); break;
+        case 28: FM_LAUNCH(28, 4, 4); break;
+        case 36: FM_LAUNCH(36, 4, 4); break;
+        case 44: FM_LAUNCH(44, 4, 3); break;
+        case 52: FM_LAUNCH(52, 4, 2); break;
         default: return 1;
     }
 #undef FM_CASE

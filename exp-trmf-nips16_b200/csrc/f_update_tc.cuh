@@ -448,7 +448,7 @@ f_update_tc_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict_
 #pragma unroll
         for (int u = 0; u < TPP; ++u) { row0[u] = ld_row(w0, u); row1[u] = ld_row(w1, u); yv0[u] = ld_yv(w0, u); }
         TC_TDECL();
-        uint32_t pend[DEPTH];       // slots of the chunks in flight, oldest first (constant indices only: registers)
+        uint32_t pend[DEPTH] = {};    // slots of the chunks in flight, oldest first (constant indices only: registers)
         int npend = 0;
         auto retire = [&]() {       // this warp's tiles of the oldest chunk in flight have landed: publish them
             fence_proxy_async();
@@ -690,4 +690,69 @@ static inline bool f_update_tc_supported(int k) {
     return false;
 }
 
+// Launch of the tcgen05 Gram pipeline: same contract as f_update_mma_launch (f_update_mma.cuh) for MODE_DEFER / MODE_GRAD.
+// `Xh` receives the pre-split fp16 copy of the gathered factor (max rows x 32 ceil(k/8) bytes: the session's Xs buffer serves when
+// 8 divides k); queue[0] is unused here, queue[8 .. 8+k) = per-column max |x|, queue[256 .. 256+k) = per-column max |w| (MODE_GRAD),
+// queue[400] = max |y|; ysc = 2 floats.  The setmaxnreg arithmetic of the kernel assumes ptxas' launch allocation: it is checked
+// against cudaFuncGetAttributes once per instantiation, and the launch is refused (return 2) if it does not hold.
+template <int K, int MODE>
+static inline int f_update_tc_launch_k(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const float *val, const float *X,
+                                       size_t xrows, void *Xh, float *invs, float *F, float *Gout, uint32_t nseries, unsigned *queue,
+                                       float *ysc, unsigned long long *launches, const float *Wv, int gaccum, double *frow, bool rescale) {
+    typedef tc::Cfg<K> C;
+    constexpr bool GRAD = MODE == tc::MODE_GRAD;
+    auto kfn = tc::f_update_tc_kernel<K, MODE>;
+    static int checked = 0;     // 0 = not yet, 1 = ok, -1 = refused
+    if (checked == 0) {
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, kfn) != cudaSuccess) return 1;
+        checked = fa.numRegs == C::launch_regs(GRAD) ? 1 : -1;
+        if (checked == 1 && cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem) != cudaSuccess) return 1;
+    }
+    if (checked < 0) return 2;
+    if (rescale) {
+        if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * 512, st) != cudaSuccess) return 1;
+        const size_t total = xrows * (size_t)K;
+        unsigned g1 = (unsigned)((total + 255) / 256);
+        if (g1 > (unsigned)(4 * num_sms)) g1 = (unsigned)(4 * num_sms);
+        if (g1 == 0) g1 = 1;
+        fm::colscale_max_kernel<<<g1, 256, 0, st>>>(X, xrows, K, queue + 8);
+        tc::presplit_kernel<<<g1, 256, sizeof(float) * K, st>>>(X, xrows, K, C::NG, queue + 8, reinterpret_cast<__half *>(Xh), invs);
+        *launches += 2;
+    } else if (cudaMemsetAsync(queue + 400, 0, sizeof(unsigned), st) != cudaSuccess) return 1;
+    tc::absmax_range_kernel<<<2 * num_sms, 256, 0, st>>>(val, ptr, nseries, queue + 400);
+    if (GRAD) {
+        const size_t total = (size_t)nseries * K;
+        unsigned g1 = (unsigned)((total + 255) / 256);
+        if (g1 > (unsigned)(4 * num_sms)) g1 = (unsigned)(4 * num_sms);
+        if (g1 == 0) g1 = 1;
+        fm::colscale_max_kernel<<<g1, 256, 0, st>>>(Wv, nseries, K, queue + 256);
+        ++*launches;
+    }
+    tc::weight_scale_kernel<<<1, 1, 0, st>>>(queue + 400, GRAD ? queue + 8 : nullptr, GRAD ? queue + 256 : nullptr, K, ysc);
+    unsigned grid = (unsigned)num_sms;
+    if (grid > nseries) grid = nseries;
+    kfn<<<grid ? grid : 1, 32 * C::nwarps(GRAD), C::smem, st>>>(ptr, idx, val, reinterpret_cast<const unsigned char *>(Xh), invs, F, Gout, nseries, Wv,
+                                                                gaccum, frow, ysc);
+    *launches += 3;
+    return cudaGetLastError() != cudaSuccess;
+}
+template <int MODE>
+static inline int f_update_tc_launch(cudaStream_t st, int num_sms, const uint64_t *ptr, const uint32_t *idx, const float *val, const float *X,
+                                     size_t xrows, void *Xh, float *invs, float *F, float *Gout, int k, uint32_t nseries, unsigned *queue,
+                                     float *ysc, unsigned long long *launches, const float *Wv = nullptr, int gaccum = 0, double *frow = nullptr,
+                                     bool rescale = true) {
+    switch (k) {
+        case 40: return f_update_tc_launch_k<40, MODE>(st, num_sms, ptr, idx, val, X, xrows, Xh, invs, F, Gout, nseries, queue, ysc, launches, Wv, gaccum, frow, rescale);
+        case 64: return f_update_tc_launch_k<64, MODE>(st, num_sms, ptr, idx, val, X, xrows, Xh, invs, F, Gout, nseries, queue, ysc, launches, Wv, gaccum, frow, rescale);
+    }
+    return 1;
+}
+
+#else   // float64 build
+
+static inline bool f_update_tc_supported(int) { return false; }
+template <int MODE>
+static inline int f_update_tc_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, void *, float *, V *, V *, int,
+                                     uint32_t, unsigned *, float *, unsigned long long *, const V * = nullptr, int = 0, double * = nullptr, bool = true) { return 1; }
 #endif   // TRMF_F32

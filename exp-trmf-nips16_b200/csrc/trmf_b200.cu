@@ -11,6 +11,7 @@
 #include "f_update.cuh"
 #include "f_update_tiled.cuh"
 #include "f_update_mma.cuh"
+#include "f_update_tc.cuh"
 #include "x_update.cuh"
 #include "x_pass_fast.cuh"
 #include "lag_update.cuh"
@@ -143,6 +144,7 @@ struct trmf_b200_session {
     V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
     V *Xs = nullptr;                  // column-scaled copy of the factor the mma Gram kernel reads (max(T, n) x k)
     float *invs = nullptr;            // its k inverse scales
+    float *ysc = nullptr;             // tcgen05 kernel: power-of-two scale of the weights and its inverse
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
     size_t sys_batch = 0;             // series per batch
@@ -413,7 +415,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->frow); dev_free(s->sys);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -562,12 +564,11 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                 return 0;
             };
             const size_t nsl = s->slab_j.size() - 1;
-            // host-packed indices: the first value slabs go out, the host cores pack the index bitmaps meanwhile, the bitmaps follow
-            // on the same copy stream (so they never queue behind ALL the values), then the remaining value slabs
-            // host-packed indices: TRMF_B200_PACK_ORDER=split sends 5/8 of the value slabs, packs, sends the bitmaps on the same copy
-            // stream and then the rest (the bitmaps never queue behind all the values); the default sends every value slab at
-            // once and the bitmaps on a stream of their own, relying on a second host-to-device copy engine
-            const bool split = host_pack && getenv("TRMF_B200_PACK_ORDER") && !strcmp(getenv("TRMF_B200_PACK_ORDER"), "split");
+            // host-packed indices: 5/8 of the value slabs go out, the host cores pack meanwhile, the bitmaps follow on the same copy
+            // stream (so they never queue behind ALL the values) and then the rest of the values.  (Measured alternative,
+            // TRMF_B200_PACK_ORDER=aux: every value slab first and the bitmaps on a stream of their own -- they still wait for the
+            // one host-to-device copy engine: 20.1 against 17.7 ms end to end at C2.)
+            const bool split = host_pack && !(getenv("TRMF_B200_PACK_ORDER") && !strcmp(getenv("TRMF_B200_PACK_ORDER"), "aux"));
             const size_t first = split ? std::min<size_t>(nsl, (nsl * 5 + 4) / 8) : nsl;
             for (size_t b = 0; b < first; ++b) if (issue_slab(b)) return 1;
             if (host_pack) {
@@ -786,6 +787,12 @@ static int read_scalars(S *s) {
 //   generic  any k <= 128, any alignment, fp64 build (f_update.cuh)
 // TRMF_B200_F_KERNEL=mma|ffma|generic pins the choice (tests, before/after profiles).
 enum { F_KERNEL_GENERIC = 0, F_KERNEL_FFMA = 1, F_KERNEL_MMA = 2 };
+// TRMF_B200_F_KERNEL=tc routes the Gram passes of a supported rank through the tcgen05 pipeline (f_update_tc.cuh) instead of the
+// mma.sync kernel; everything around them (scaling, deferred Cholesky, Gram mat-vecs) is shared, so it counts as F_KERNEL_MMA.
+static bool use_tc(int k) {
+    const char *e = getenv("TRMF_B200_F_KERNEL");
+    return e && !strcmp(e, "tc") && f_update_tc_supported(k);
+}
 static int f_kernel_choice(int k, const V *X) {
     const char *e = getenv("TRMF_B200_F_KERNEL");
     if (getenv("TRMF_B200_GENERIC_F") || (e && !strcmp(e, "generic"))) return F_KERNEL_GENERIC;
@@ -799,7 +806,7 @@ static int f_kernel_choice(int k, const V *X) {
 // scratch of the mma Gram kernel: the column-scaled factor copy and its inverse scales
 static int mma_scratch(S *s) {
     if (s->Xs) return 0;
-    if (dev_alloc(&s->Xs, std::max(Tcap(s), s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->frow, Tcap(s))) return 1;
+    if (dev_alloc(&s->Xs, std::max(Tcap(s), s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->ysc, 2) || dev_alloc(&s->frow, Tcap(s))) return 1;
     return 0;
 }
 
@@ -1017,7 +1024,8 @@ static int gram_matvec(S *s, const V *v, V *out, bool accum, double *dhd, const 
         // k >= 56: four warps per CTA (the per-warp fp64 partials of a k x k Gram must fit 48 KB of static shared memory)
 #define GM_CASE4(KK) case KK: { const unsigned g4 = (unsigned)std::max<size_t>(1, std::min<size_t>((s->T + 3) / 4, (size_t)s->num_sms * 12)); \
         LAUNCH(s, (gram_matvec4_kernel<KK, 4>), g4, 128, 0, s->Gt, v, out, s->T, accum, s->part, s->ticket, dhd, gate); return 0; }
-        switch (k) { GM_CASE(8) GM_CASE(16) GM_CASE(20) GM_CASE(24) GM_CASE(32) GM_CASE(40) GM_CASE(48) GM_CASE4(56) GM_CASE4(60) GM_CASE4(64) default: break; }
+        switch (k) { GM_CASE(8) GM_CASE(12) GM_CASE(16) GM_CASE(20) GM_CASE(24) GM_CASE(28) GM_CASE(32) GM_CASE(36) GM_CASE(40) GM_CASE(44) GM_CASE(48)
+                     GM_CASE4(52) GM_CASE4(56) GM_CASE4(60) GM_CASE4(64) default: break; }
 #undef GM_CASE4
 #undef GM_CASE
     }
@@ -1062,6 +1070,16 @@ static int mma_f_range(S *s, size_t j0, size_t j1, bool rescale) {
     }
     for (size_t b0 = j0; b0 < j1; b0 += s->sys_batch) {
         const size_t b1 = std::min(j1, b0 + s->sys_batch);
+        if (use_tc(k)) {
+            const int rc = f_update_tc_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+                                                              s->H + b0 * (size_t)k, (V *)nullptr, k, (uint32_t)(b1 - b0), s->queue, s->ysc,
+                                                              &s->launches, nullptr, 0, s->sys, rescale && b0 == j0);
+            if (rc == 2) return fail("tcgen05 Gram kernel: ptxas' register allocation differs from the kernel's setmaxnreg plan; unset TRMF_B200_F_KERNEL");
+            if (rc || f_update_mma_solve(s->stream, s->num_sms, s->col_ptr + b0, s->sys, s->H + b0 * (size_t)k, k, s->lambdaI, (uint32_t)(b1 - b0),
+                                         &s->launches))
+                return fail("f_update_tc launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            continue;
+        }
         if (f_update_mma_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
                                                 s->H + b0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(b1 - b0), s->queue,
                                                 &s->launches, nullptr, 0, s->sys, rescale && b0 == j0) ||
@@ -1181,6 +1199,11 @@ extern "C" int trmf_b200_x_update(S *s) {
                     LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR, (const int *)nullptr);
                     const bool one = s->world == 1;
                     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev4, s->stream));
+                    if (use_tc(s->k))
+                        rc = f_update_tc_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
+                                                               one ? s->g : s->part_tk, s->Gt, s->k, (uint32_t)s->T, s->queue, s->ysc, &s->launches,
+                                                               s->W, one ? 1 : 0, s->frow);
+                    else
                     rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
                                                             one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
                                                             s->W, one ? 1 : 0, s->frow);

@@ -196,8 +196,7 @@ pass_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ col, 
 }   // namespace xp
 
 static inline bool x_pass_fast_supported(int k) {
-    switch (k) { case 8: case 16: case 20: case 24: case 32: case 40: case 48: case 56: case 60: case 64: return true; }
-    return false;
+    return k >= 8 && k <= 64 && k % 4 == 0;
 }
 
 template <int MODE>
@@ -220,7 +219,8 @@ static inline int x_pass_fast_launch(cudaStream_t st, int num_sms, const uint64_
         break;                                                                                               \
     }
     switch (k) {
-        XP_CASE(8) XP_CASE(16) XP_CASE(20) XP_CASE(24) XP_CASE(32) XP_CASE(40) XP_CASE(48) XP_CASE(56) XP_CASE(60) XP_CASE(64)
+        XP_CASE(8) XP_CASE(12) XP_CASE(16) XP_CASE(20) XP_CASE(24) XP_CASE(28) XP_CASE(32) XP_CASE(36) XP_CASE(40) XP_CASE(44) XP_CASE(48) XP_CASE(52)
+        XP_CASE(56) XP_CASE(60) XP_CASE(64)
         default: return 1;
     }
 #undef XP_CASE

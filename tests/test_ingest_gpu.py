@@ -190,3 +190,32 @@ def test_host_packed_index_upload_trains_identically(monkeypatch):
     for other in outs[1:]:
         for a, b in zip(outs[0], other):
             assert np.array_equal(a, b)
+
+
+def test_slab_upload_of_a_thin_matrix_is_not_packed_and_trains_identically(monkeypatch):
+    """Below 1/8 density the per-series bitmaps would not pay (n * ceil(T/32) * 4 bytes > nnz): the slab upload sends plain
+    indices.  (Round-2 regression: this path once issued only 5 of its 8 slabs.)  Same factors as a single-copy upload."""
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    dtype = np.float32
+    rng = np.random.RandomState(9)
+    T, n, k = 20000, 3000, 16
+    Y = sps.random(T, n, density=0.075, format="csc", random_state=rng, dtype=np.float64)
+    Y.data = (rng.randn(Y.nnz) + 3.0)
+    Y = Y.astype(dtype)
+    Y.sort_indices()
+    assert Y.nnz >= (1 << 22) and n * ((T + 31) // 32) * 4 > Y.nnz
+    lags = np.array([1, 7, 24], dtype=np.uint32)
+    W0, H0, L0 = rng.rand(T, k).astype(dtype), rng.rand(n, k).astype(dtype), rng.randn(3, k).astype(dtype)
+    outs = []
+    for slabs in (True, False):
+        if slabs:
+            monkeypatch.delenv("TRMF_B200_NO_SLAB_UPLOAD", raising=False)
+        else:
+            monkeypatch.setenv("TRMF_B200_NO_SLAB_UPLOAD", "1")
+        s = Session(PyMatrix(Y, dtype, twin=False), lags, W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+        s.train(max_iter=1, period_W=1, period_H=1, period_Lag=1)
+        outs.append(s.download())
+        s.close()
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
