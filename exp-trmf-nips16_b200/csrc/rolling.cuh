@@ -289,6 +289,41 @@ extern "C" S *trmf_b200_roll_create(const PyMatrix *Y, const uint32_t *lag_set, 
     return s;
 }
 
+// Per-series mean and standard deviation over the first T_w time stamps of a DENSE resident Y -- the statistics of the reference's
+// NormalizedTransform (trmf.py:84-88: Yd.mean(axis=0), Yd.std(axis=0)), bit for bit: NumPy reduces along axis 0 of a C-ordered
+// array by adding row after row into one accumulator per column, in the array's own precision; std is sqrt(mean((y - mean)^2))
+// with every operation rounded separately.  One thread per series walks the rows in that order (loads coalesced across series).
+template <typename VT>
+__global__ void roll_stats_kernel(const VT *__restrict__ Y, uint64_t Tw, uint64_t n, VT *__restrict__ mean_out, VT *__restrict__ std_out) {
+    const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    VT acc = (VT)0;
+    for (uint64_t i = 0; i < Tw; ++i) acc = acc + Y[i * n + j];
+    const VT mean = acc / (VT)Tw;
+    VT sq = (VT)0;
+    for (uint64_t i = 0; i < Tw; ++i) {
+        const VT d = Y[i * n + j] - mean;
+        sq = sq + d * d;
+    }
+    mean_out[j] = mean;
+    std_out[j] = (VT)sqrt((double)(sq / (VT)Tw));   // (sqrt of a float rounded from the correctly rounded double sqrt = sqrtf)
+}
+
+extern "C" int trmf_b200_roll_stats(S *s, uint64_t T_window, void *mean_host, void *std_host) {
+    g_last_error.clear();
+    if (!s->rolling || s->R_Yd == nullptr) return fail("roll_stats: needs a rolling session with a dense resident Y");
+    if (T_window == 0 || T_window > s->T_cap) return fail("roll_stats: window of %llu time stamps outside the resident %zu", (unsigned long long)T_window, s->T_cap);
+    CUDA_TRY(cudaSetDevice(s->device));
+    V *d = nullptr;
+    if (dev_alloc(&d, 2 * s->n)) return 1;
+    LAUNCH(s, roll_stats_kernel<V>, (unsigned)((s->n + 63) / 64), 64, 0, s->R_Yd, T_window, (uint64_t)s->n, d, d + s->n);
+    CUDA_TRY(cudaMemcpyAsync(mean_host, d, s->n * sizeof(V), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaMemcpyAsync(std_host, d + s->n, s->n * sizeof(V), cudaMemcpyDeviceToHost, s->stream));
+    CUDA_TRY(cudaStreamSynchronize(s->stream));
+    dev_free(d);
+    return 0;
+}
+
 extern "C" int trmf_b200_roll_window(S *s, uint64_t T_window, const void *scale, const void *offset) {
     g_last_error.clear();
     return roll_window_impl(s, T_window, scale, offset);

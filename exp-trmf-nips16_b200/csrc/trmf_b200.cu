@@ -289,7 +289,9 @@ __attribute__((target("avx2"))) static void pack_series_avx2(const uint32_t *r, 
     pack_series_scalar(r + i, cnt - i, w);
 }
 #endif
-static void pack_bitmap_host(const uint64_t *col_ptr, const uint32_t *row_idx, size_t n, uint32_t words, uint32_t *out) {
+// Returns false when some series' row indices are not strictly ascending (unsorted arrays or duplicate entries are legal input for
+// the reference's core, which never looks at their order): a bitmap cannot carry those, the caller uploads plain indices instead.
+static bool pack_bitmap_host(const uint64_t *col_ptr, const uint32_t *row_idx, size_t n, uint32_t words, uint64_t rows, uint32_t *out) {
     unsigned nt = std::thread::hardware_concurrency();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= (unsigned)std::max(1, atoi(e));   // one process per GPU: share the host cores
     if (const char *e = getenv("TRMF_B200_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
@@ -299,16 +301,23 @@ static void pack_bitmap_host(const uint64_t *col_ptr, const uint32_t *row_idx, s
     if (__builtin_cpu_supports("avx2") && !getenv("TRMF_B200_PACK_SCALAR")) pack = pack_series_avx2;
 #endif
     std::atomic<size_t> next(0);
+    std::atomic<bool> bad(false);
     const size_t chunk = 32;
     auto work = [&]() {
         for (;;) {
             const size_t j0 = next.fetch_add(chunk);
-            if (j0 >= n) return;
+            if (j0 >= n || bad.load(std::memory_order_relaxed)) return;
             const size_t j1 = std::min(n, j0 + chunk);
             for (size_t j = j0; j < j1; ++j) {
                 uint32_t *w = out + j * (size_t)words;
                 memset(w, 0, (size_t)words * sizeof(uint32_t));
-                pack(row_idx + col_ptr[j], (size_t)(col_ptr[j + 1] - col_ptr[j]), w);
+                const uint32_t *r = row_idx + col_ptr[j];
+                const size_t cnt = (size_t)(col_ptr[j + 1] - col_ptr[j]);
+                unsigned ok = 1;
+                for (size_t i = 0; i + 1 < cnt; ++i) ok &= (unsigned)(r[i] < r[i + 1]);
+                if (cnt && (uint64_t)r[cnt - 1] >= rows) ok = 0;
+                if (!ok) { bad.store(true, std::memory_order_relaxed); return; }
+                pack(r, cnt, w);
             }
         }
     };
@@ -316,6 +325,7 @@ static void pack_bitmap_host(const uint64_t *col_ptr, const uint32_t *row_idx, s
     for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
     work();
     for (auto &t : th) t.join();
+    return !bad.load();
 }
 
 // --------------------------------------------------------------------------
@@ -583,13 +593,19 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                 }
                 CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));             // (bm_dev's allocation is ordered on s->stream)
                 CUDA_TRY(cudaStreamWaitEvent(bst, s->csr_ready, 0));
-                pack_bitmap_host(Y->col_ptr, Y->row_idx, s->n, bm_words, s->pack_buf);
-                CUDA_TRY(cudaMemcpyAsync(bm_dev, s->pack_buf, bytes, cudaMemcpyHostToDevice, bst));
-                CUDA_TRY(cudaEventRecord(s->csr_ready, bst));
-                CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
-                bitmap_expand_kernel<<<(unsigned)(s->num_sms * 8), 256, 0, s->stream>>>(s->col_ptr, bm_dev, s->n, s->T, bm_words, s->row_idx);
-                s->launches++;
-                CUDA_TRY(cudaGetLastError());
+                if (pack_bitmap_host(Y->col_ptr, Y->row_idx, s->n, bm_words, s->T, s->pack_buf)) {
+                    CUDA_TRY(cudaMemcpyAsync(bm_dev, s->pack_buf, bytes, cudaMemcpyHostToDevice, bst));
+                    CUDA_TRY(cudaEventRecord(s->csr_ready, bst));
+                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
+                    bitmap_expand_kernel<<<(unsigned)(s->num_sms * 8), 256, 0, s->stream>>>(s->col_ptr, bm_dev, s->n, s->T, bm_words, s->row_idx);
+                    s->launches++;
+                    CUDA_TRY(cudaGetLastError());
+                } else {
+                    // unsorted or duplicate indices: the whole row_idx array goes over as it is, before anything reads it
+                    CUDA_TRY(cudaMemcpyAsync(s->row_idx, Y->row_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, bst));
+                    CUDA_TRY(cudaEventRecord(s->csr_ready, bst));
+                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
+                }
                 dev_free(bm_dev);
                 for (size_t b = first; b < nsl; ++b) if (issue_slab(b)) return 1;
             }

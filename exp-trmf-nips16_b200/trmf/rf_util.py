@@ -124,9 +124,11 @@ class PyMatrix(ctypes.Structure):
         self.rows, self.cols = int(A.shape[0]), int(A.shape[1])
         if sps.issparse(A):
             if A.format == "coo":
-                # explicit COO keeps duplicates apart in the reference (rf_util.py:100-119);
-                # here they are summed, which is what every caller in trmf.py relies on.
-                A = A.tocsr()
+                # explicit COO: duplicate (i, j) entries stay separate observations, as in the reference (rf_util.py:100-119:
+                # bincount + argsort(row * ncols + col), nnz = len(data)); scipy's own conversions would sum them
+                self._init_from_coo(A, dtype, twin, pack)
+                self._bind()
+                return
             self.type = PyMatrix.SPARSE
             want_csr = (twin or A.format != "csc") and not pack
             want_csc = twin or A.format == "csc" or pack
@@ -161,13 +163,37 @@ class PyMatrix(ctypes.Structure):
             self.nnz = self.rows * self.cols
         else:
             raise TypeError("PyMatrix expects a numpy.ndarray or a scipy.sparse matrix, got {}".format(type(A)))
+        self._bind()
+
+    def _bind(self):
         fields = dict(PyMatrix._fields_)
-        for name, arr in buf.items():
+        for name, arr in self.py_buf.items():
             ctype = fields[name]
             if ctype is ctypes.c_void_p:
                 setattr(self, name, arr.ctypes.data)
             else:
                 setattr(self, name, arr.ctypes.data_as(ctype))
+
+    def _init_from_coo(self, coo, dtype, twin, pack):
+        def compress(major, minor, nmajor, nminor):
+            indptr = np.cumsum(np.bincount(major.astype(np.int64) + 1, minlength=nmajor + 1), dtype=np.uint64)
+            order = np.argsort(major.astype(np.int64) * nminor + minor.astype(np.int64), kind="stable")
+            return indptr, minor[order].astype(np.uint32), coo.data[order].astype(dtype)
+        buf = self.py_buf
+        self.type = PyMatrix.SPARSE
+        self.nnz = int(coo.data.shape[0])
+        dup = self.nnz != len(np.unique(coo.row.astype(np.int64) * self.cols + coo.col.astype(np.int64)))
+        if pack and dup:
+            raise ValueError("pack=True cannot represent duplicate (row, col) entries of a COO matrix")
+        if twin or not pack:     # CSR (the orientation a COO matrix is closest to); with twin also the CSC
+            buf["row_ptr"], buf["col_idx"], buf["val_t"] = compress(coo.row, coo.col, self.rows, self.cols)
+        if twin or pack:
+            buf["col_ptr"], buf["row_idx"], buf["val"] = compress(coo.col, coo.row, self.cols, self.rows)
+        if pack:
+            for name in ("row_ptr", "col_idx", "val_t"):
+                buf.pop(name, None)
+            buf["row_idx"] = pack_bitmap(buf["col_ptr"], buf["row_idx"], self.rows)
+            self.type = PyMatrix.SPARSE_BITMAP
 
     @classmethod
     def identity(cls, size, dtype=np.float32):

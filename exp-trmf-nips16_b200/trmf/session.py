@@ -239,6 +239,7 @@ class RollingSession(Session):
                                            self.k, int(bool(missing)), device)
         if not self.h:
             raise RuntimeError("trmf (CUDA) roll_create failed: " + lib.trmf_b200_last_error().decode())
+        self.dense_resident = self.pyY.type in (PyMatrix.DENSE_ROWMAJOR, PyMatrix.DENSE_COLMAJOR) and not missing
         self.pyY = None   # the device holds Y now; let the host marshalling copies go
         self.set_params(lambdaI, lambdaAR, lambdaLag)
 
@@ -255,6 +256,18 @@ class RollingSession(Session):
             return a.ctypes.data
         _check(self.lib, self.lib.trmf_b200_roll_window(self.h, int(T_w), ptr(scale), ptr(offset)), "roll_window")
         self.T = int(T_w)
+
+    def window_stats(self, T_w):
+        """(mean, std) per series over ``Y[:T_w]`` of a dense resident Y, computed on the device in NumPy's axis-0 summation
+        order -- bit-identical to ``Y[:T_w].mean(axis=0)``, ``Y[:T_w].std(axis=0)`` (reference trmf.py:84-88).  Returns None
+        when the session does not hold a dense copy of Y (sparse-born or sparsified sessions)."""
+        if not self.dense_resident:
+            return None
+        mean = np.empty(self.n, dtype=self.dtype)
+        std = np.empty(self.n, dtype=self.dtype)
+        self.lib.trmf_b200_roll_stats.argtypes = [c_void_p, c_uint64, c_void_p, c_void_p]
+        _check(self.lib, self.lib.trmf_b200_roll_stats(self.h, int(T_w), mean.ctypes.data, std.ctypes.data), "roll_stats")
+        return mean, std
 
     @property
     def nnz(self):

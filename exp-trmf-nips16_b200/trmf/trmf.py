@@ -90,10 +90,14 @@ class NormalizedTransform(object):
     """Per-series affine normalisation y -> a*y + b with a = 1/std, b = -mean/std
     over time; zero std is treated as 1 (reference trmf.py:82-96)."""
 
-    def __init__(self, Y):
-        Yd = Y.toarray() if smat.issparse(Y) else np.asarray(Y)
-        mean = Yd.mean(axis=0).reshape(1, -1)
-        std = Yd.std(axis=0).reshape(1, -1).copy()
+    def __init__(self, Y, _stats=None):
+        if _stats is not None:      # (mean, std) of Y's columns, already computed (on the device: session.RollingSession.window_stats)
+            mean, std = (np.asarray(x).reshape(1, -1) for x in _stats)
+            std = std.copy()
+        else:
+            Yd = Y.toarray() if smat.issparse(Y) else np.asarray(Y)
+            mean = Yd.mean(axis=0).reshape(1, -1)
+            std = Yd.std(axis=0).reshape(1, -1).copy()
         std[std == 0] = 1.0
         self.a = 1.0 / std
         self.b = -self.a * mean
@@ -228,7 +232,7 @@ class Model(object):
 
     # ---- initialisation / warm start (trmf.py:222-251) ----
     @classmethod
-    def initialize(cls, Y, lag_set, k, warm_start_model=None, seed=None, dtype=None, transform=None):
+    def initialize(cls, Y, lag_set, k, warm_start_model=None, seed=None, dtype=None, transform=None, _transform_stats=None):
         if seed is not None:
             np.random.seed(seed)
         if dtype is None:
@@ -254,7 +258,7 @@ class Model(object):
             lag_val[:] = prev.lag_val
             transform = prev.transform
         if transform is not None:
-            transform = NormalizedTransform(Y)
+            transform = NormalizedTransform(Y, _stats=_transform_stats)
         pyW, pyH, pyL = cls._wrap(W, H, lag_val, dtype)
         return cls(pyW=pyW, pyH=pyH, pylag_val=pyL, lag_set=lag_set, transform=transform)
 
@@ -407,8 +411,12 @@ def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR,
             trn_end = T - (nr_windows - w) * window_size
             # the dense slice stands in for csr_matrix(Y_trn): initialize() only takes its shape, dtype and
             # NormalizedTransform statistics, which the reference computes on toarray() anyway (trmf.py:84)
+            # the window statistics of NormalizedTransform (a fresh one per window, trmf.py:247-248) come from the device when it
+            # holds the dense Y: same bits as Yd.mean / Yd.std, without two host passes over the whole prefix per window
+            will_transform = (prev_model.transform if prev_model is not None else transform) is not None
+            stats = sess.window_stats(trn_end) if will_transform else None
             curr_model = Model.initialize(Y[:trn_end, :], lag_set, k, seed=seed, warm_start_model=prev_model,
-                                          transform=transform)
+                                          transform=transform, _transform_stats=stats)
             tr = curr_model.transform
             sess.window(trn_end, None if tr is None else tr.a, None if tr is None else tr.b)
             if prev_model is None:

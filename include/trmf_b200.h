@@ -211,6 +211,10 @@ int  trmf_b200_bitmap_expand(uint64_t T, uint64_t n, uint64_t nnz, const uint64_
 trmf_b200_session *trmf_b200_roll_create(const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size, uint32_t k,
                                          int32_t missing, int32_t device);
 int trmf_b200_roll_window(trmf_b200_session *s, uint64_t T_window, const void *scale, const void *offset);
+/* Per-series mean and standard deviation over Y[:T_window] of a rolling session with a DENSE resident Y (n values of the
+ * library's ValueType each, host buffers): the statistics of the reference's NormalizedTransform (trmf.py:84-88), computed on the
+ * device in NumPy's summation order, bit-identical to Yd.mean(axis=0) / Yd.std(axis=0). */
+int trmf_b200_roll_stats(trmf_b200_session *s, uint64_t T_window, void *mean_host, void *std_host);
 /* rows [row0, row0+nrows) of W from / to a host buffer of nrows x k values (any session) */
 int trmf_b200_upload_W_rows(trmf_b200_session *s, uint64_t row0, uint64_t nrows, const void *src);
 int trmf_b200_download_W_rows(trmf_b200_session *s, uint64_t row0, uint64_t nrows, void *dst);

@@ -203,3 +203,29 @@ def test_pack_bitmap_is_the_per_series_mask():
     pm = PyMatrix(m, np.float32, twin=False, pack=True)
     assert pm.type == PyMatrix.SPARSE_BITMAP == 5 and not pm.row_ptr and not pm.col_idx and not pm.val_t
     assert len(pm.py_buf["row_idx"]) == n * ((T + 31) // 32) and pm.nnz == m.nnz
+
+
+def test_coo_pymatrix_keeps_duplicate_entries_like_the_reference():
+    """reference rf_util.py:100-119: a coo_matrix goes through bincount + argsort(row * ncols + col), so duplicate (i, j)
+    entries stay separate observations and nnz = len(data); scipy's tocsr() would sum them."""
+    import scipy.sparse as sps
+    from trmf.rf_util import PyMatrix
+    rng = np.random.RandomState(1)
+    T, n, m = 40, 30, 500
+    row, col, val = rng.randint(0, T, m), rng.randint(0, n, m), rng.randn(m)
+    coo = sps.coo_matrix((val, (row, col)), shape=(T, n))
+    assert coo.tocsr().nnz < m                      # there are duplicates
+    pm = PyMatrix(coo, np.float64)
+    assert pm.nnz == m and pm.type == PyMatrix.SPARSE
+    b = pm.py_buf
+
+    def ref(major, minor, nmajor, nminor):          # the reference's coo_to_csr, stable
+        indptr = np.cumsum(np.bincount(major + 1, minlength=nmajor + 1)).astype(np.uint64)
+        order = np.argsort(major * nminor + minor, kind="stable")
+        return indptr, minor[order].astype(np.uint32), val[order]
+    for got, want in zip((b["row_ptr"], b["col_idx"], b["val_t"]), ref(row, col, T, n)):
+        assert np.array_equal(got, want)
+    for got, want in zip((b["col_ptr"], b["row_idx"], b["val"]), ref(col, row, n, T)):
+        assert np.array_equal(got, want)
+    with pytest.raises(ValueError):
+        PyMatrix(coo, np.float64, pack=True)

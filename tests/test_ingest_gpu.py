@@ -219,3 +219,69 @@ def test_slab_upload_of_a_thin_matrix_is_not_packed_and_trains_identically(monke
         s.close()
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_coo_with_duplicates_trains_like_the_reference_core():
+    """Duplicate (i, j) entries of a COO matrix are separate observations in the reference (rf_util.py:100-119); the same
+    PyMatrix struct is handed to the compiled reference core and to the CUDA library (float64, one outer iteration)."""
+    import ctypes
+    from oracle import abi
+    from trmf.rf_util import PyMatrix
+    from trmf.session import _lib
+    if not abi.ref_available(np.float64):
+        pytest.skip("oracle/_ref did not travel")
+    rng = np.random.RandomState(2)
+    T, n, k, m = 120, 80, 8, 6000
+    row, col = rng.randint(0, T, m), rng.randint(0, n, m)
+    coo = sps.coo_matrix((rng.randn(m) + 2.0, (row, col)), shape=(T, n))
+    assert coo.tocsr().nnz < m
+    lags = np.array([1, 2, 5], dtype=np.uint32)
+    W0, H0, L0 = rng.rand(T, k), rng.rand(n, k), rng.randn(3, k)
+    outs = []
+    for which in ("reference", "cuda"):
+        lib = abi.load(abi.ref_lib_path(np.float64)) if which == "reference" else _lib(np.float64)
+        pY = PyMatrix(coo, np.float64)
+        pW, pH = PyMatrix(W0.copy(), np.float64, major="row"), PyMatrix(H0.copy(), np.float64, major="row")
+        pL = PyMatrix(np.asfortranarray(L0.copy()), np.float64, major="col")
+        lib.c_trmf_train.restype = None
+        lib.c_trmf_train(ctypes.byref(pY), lags.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), ctypes.c_uint32(3), ctypes.byref(pW),
+                         ctypes.byref(pH), ctypes.byref(pL), ctypes.c_int(1), ctypes.c_double(0.5), ctypes.c_double(5.0), ctypes.c_double(0.5),
+                         ctypes.c_int32(1), ctypes.c_int32(1), ctypes.c_int32(1), ctypes.c_int32(1), ctypes.c_int32(2), ctypes.c_int32(1),
+                         ctypes.c_int32(0))
+        outs.append((pW.py_buf["val"].copy(), pH.py_buf["val"].copy(), pL.py_buf["val"].copy()))
+    for a, b in zip(*outs):
+        assert cases.rel(b, a) < 1e-9
+
+
+def test_host_packing_declines_unsorted_indices(monkeypatch):
+    """The C ABI takes the CSC arrays as they are (the reference's core never looks at the order inside a series).  A bitmap
+    cannot carry an unsorted series: the in-call host packing must notice and send plain indices -- same factors as with the
+    packing switched off."""
+    from trmf.rf_util import PyMatrix
+    from trmf.session import Session
+    dtype = np.float32
+    rng = np.random.RandomState(6)
+    T, n, k = 3001, 2300, 16
+    Y = sps.csc_matrix(np.where(rng.rand(T, n) < 0.7, rng.randn(T, n) + 3.0, 0.0).astype(dtype))
+    Y.sort_indices()
+    assert Y.nnz >= (1 << 22)
+    pm = PyMatrix(Y, dtype, twin=False)
+    ri, va, cp = pm.py_buf["row_idx"], pm.py_buf["val"], pm.py_buf["col_ptr"].astype(np.int64)
+    j = 1234                                        # swap two entries of one series (indices and values alike)
+    a, b = cp[j] + 3, cp[j] + 9
+    ri[[a, b]] = ri[[b, a]]
+    va[[a, b]] = va[[b, a]]
+    lags = np.array([1, 7, 24], dtype=np.uint32)
+    W0, H0, L0 = rng.rand(T, k).astype(dtype), rng.rand(n, k).astype(dtype), rng.randn(3, k).astype(dtype)
+    outs = []
+    for pack in (True, False):
+        if pack:
+            monkeypatch.delenv("TRMF_B200_NO_HOST_PACK", raising=False)
+        else:
+            monkeypatch.setenv("TRMF_B200_NO_HOST_PACK", "1")
+        s = Session(pm, lags, W0, H0, L0, missing=True, dtype=dtype, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+        s.train(max_iter=1, period_W=1, period_H=1, period_Lag=1)
+        outs.append(s.download())
+        s.close()
+    for x, y in zip(*outs):
+        assert np.array_equal(x, y)

@@ -51,6 +51,11 @@ class FakeRollingSession(object):
     def set_params(self, lambdaI, lambdaAR, lambdaLag):
         self.lams = (lambdaI, lambdaAR, lambdaLag)
 
+    def window_stats(self, T_w):
+        if sps.issparse(self.Y):
+            return None
+        return self.Y[:T_w].mean(axis=0), self.Y[:T_w].std(axis=0)
+
     def window(self, T_w, scale=None, offset=None):
         assert 0 < T_w <= self.T_cap and not self.closed
         self.T = T_w

@@ -159,6 +159,23 @@ def test_grid_search_over_one_resident_copy():
     assert len({r["metrics"].nd for r in res}) == 4          # the weights did reach the device
 
 
+def test_grid_search_matches_the_oracle_loop(monkeypatch, capsys):
+    """grid_search (reference trmf.py:331-346) over a grid in k, window_size and the weights -- resident sessions shared where
+    the key allows, reordered internally -- against the reference's own loop order with the NumPy oracle doing every fit
+    (float64): same metrics per grid point, same best point, results in the grid's order."""
+    Y = series(200, 18, seed=12)
+    grid = {"k": [3, 5], "lambdaAR": [5.0, 50.0], "window_size": [6, 8]}
+    kw = dict(nr_windows=2, max_iter=3, missing=True, transform=True, lambdaI=0.5, lambdaLag=0.5)
+    res, best = trmf.grid_search(Y, [1, 2, 12], grid, resident=True, **kw)
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    ora, best_ora = trmf.grid_search(Y, [1, 2, 12], grid, resident=False, **kw)
+    assert [r["kws"] for r in res] == [r["kws"] for r in ora] and len(res) == 8
+    for r, o in zip(res, ora):
+        for got, want in zip(r["metrics"], o["metrics"]):
+            assert abs(got - want) <= 1e-7 * abs(want)
+    assert [r["metrics"].m_nd for r in res].index(best.m_nd) == [o["metrics"].m_nd for o in ora].index(best_ora.m_nd)
+
+
 @pytest.mark.parametrize("name", ["missing", "missing_tr", "full", "full_tr"])
 @pytest.mark.parametrize("resident", [True, False])
 def test_rolling_validate_matches_fits_by_the_reference_core(name, resident):
@@ -173,3 +190,28 @@ def test_rolling_validate_matches_fits_by_the_reference_core(name, resident):
                                 _models_out=models, **kw)
     check_models_against_golden(g, name, models, 1e-8)
     assert np.allclose(np.array(list(met)), g[name + "_metrics"], rtol=1e-7, atol=0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_window_statistics_on_the_device_are_numpys_bits(dtype):
+    """NormalizedTransform's per-window statistics (reference trmf.py:84-88) for a dense resident Y: computed on the device in
+    NumPy's axis-0 summation order -> bit-equal mean / std, hence bit-equal a, b, at the electricity shape."""
+    import trmf
+    from trmf.session import RollingSession
+    rng = np.random.RandomState(5)
+    T, n = 26304, 370
+    t = np.arange(T)[:, None]
+    Y = (np.abs(rng.randn(T, n)) * (0.5 + 20 * rng.rand(1, n)) * (1.0 + 0.5 * np.sin(2 * np.pi * t / 24.0)) + 0.1).astype(dtype)
+    Y[:, 7] = 3.25                                   # a constant series: std == 0 -> treated as 1
+    s = RollingSession(Y, list(range(1, 25)), 4, missing=False, dtype=dtype)
+    try:
+        for T_w in (T, T - 24 * 7, 1000, 1):
+            mean, std = s.window_stats(T_w)
+            assert np.array_equal(mean, Y[:T_w].mean(axis=0)) and np.array_equal(std, Y[:T_w].std(axis=0))
+            tr_dev, tr_host = trmf.NormalizedTransform(None, _stats=(mean, std)), trmf.NormalizedTransform(Y[:T_w])
+            assert np.array_equal(tr_dev.a, tr_host.a) and np.array_equal(tr_dev.b, tr_host.b)
+    finally:
+        s.close()
+    sp_sess = RollingSession(Y[:2000], [1, 2], 4, missing=True, dtype=dtype)     # sparsified on the device: no dense copy kept
+    assert sp_sess.window_stats(1000) is None
+    sp_sess.close()
