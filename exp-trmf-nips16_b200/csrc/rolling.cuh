@@ -293,17 +293,22 @@ extern "C" S *trmf_b200_roll_create(const PyMatrix *Y, const uint32_t *lag_set, 
 // NormalizedTransform (trmf.py:84-88: Yd.mean(axis=0), Yd.std(axis=0)), bit for bit: NumPy reduces along axis 0 of a C-ordered
 // array by adding row after row into one accumulator per column, in the array's own precision; std is sqrt(mean((y - mean)^2))
 // with every operation rounded separately.  One thread per series walks the rows in that order (loads coalesced across series).
+// (separately rounded multiply / add: nvcc must not contract d * d + sq into one FMA)
+__device__ __forceinline__ float stat_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double stat_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float stat_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double stat_add(double a, double b) { return __dadd_rn(a, b); }
 template <typename VT>
 __global__ void roll_stats_kernel(const VT *__restrict__ Y, uint64_t Tw, uint64_t n, VT *__restrict__ mean_out, VT *__restrict__ std_out) {
     const uint64_t j = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     if (j >= n) return;
     VT acc = (VT)0;
-    for (uint64_t i = 0; i < Tw; ++i) acc = acc + Y[i * n + j];
+    for (uint64_t i = 0; i < Tw; ++i) acc = stat_add(acc, Y[i * n + j]);
     const VT mean = acc / (VT)Tw;
     VT sq = (VT)0;
     for (uint64_t i = 0; i < Tw; ++i) {
-        const VT d = Y[i * n + j] - mean;
-        sq = sq + d * d;
+        const VT d = stat_add(Y[i * n + j], -mean);
+        sq = stat_add(sq, stat_mul(d, d));
     }
     mean_out[j] = mean;
     std_out[j] = (VT)sqrt((double)(sq / (VT)Tw));   // (sqrt of a float rounded from the correctly rounded double sqrt = sqrtf)

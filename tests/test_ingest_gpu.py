@@ -239,7 +239,8 @@ def test_coo_with_duplicates_trains_like_the_reference_core():
     W0, H0, L0 = rng.rand(T, k), rng.rand(n, k), rng.randn(3, k)
     outs = []
     for which in ("reference", "cuda"):
-        lib = abi.load(abi.ref_lib_path(np.float64)) if which == "reference" else _lib(np.float64)
+        # (plain CDLL handles without argtypes: the same PyMatrix struct goes to both libraries)
+        lib = ctypes.CDLL(abi.ref_lib_path(np.float64)) if which == "reference" else ctypes.CDLL(_lib(np.float64)._name)
         pY = PyMatrix(coo, np.float64)
         pW, pH = PyMatrix(W0.copy(), np.float64, major="row"), PyMatrix(H0.copy(), np.float64, major="row")
         pL = PyMatrix(np.asfortranarray(L0.copy()), np.float64, major="col")
