@@ -12,6 +12,7 @@
 #include "f_update_tiled.cuh"
 #include "f_update_mma.cuh"
 #include "f_update_tc.cuh"
+#include "f_update_mma2.cuh"
 #include "x_update.cuh"
 #include "x_pass_fast.cuh"
 #include "lag_update.cuh"
@@ -144,7 +145,10 @@ struct trmf_b200_session {
     V *Gt = nullptr, *bt = nullptr;   // T x k x k Grams of the series factor, T x k rhs
     V *Xs = nullptr;                  // column-scaled copy of the factor the mma Gram kernel reads (max(T, n) x k)
     float *invs = nullptr;            // its k inverse scales
-    float *ysc = nullptr;             // tcgen05 kernel: power-of-two scale of the weights and its inverse
+    float *ysc = nullptr;             // power-of-two scale of the pre-split weights (or of the tcgen05 kernel's) and its inverse
+    uint32_t *valh = nullptr;         // F-update of f_update_mma2.cuh: the CSC values as fp16 pairs (nnz words, indexed like val)
+    size_t valh_cap = 0;
+    bool valh_ok = false;             // valh / ysc describe the whole of the current val (cleared whenever Y changes)
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
     size_t sys_batch = 0;             // series per batch
@@ -425,7 +429,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys); dev_free(s->valh);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -809,6 +813,12 @@ static bool use_tc(int k) {
     const char *e = getenv("TRMF_B200_F_KERNEL");
     return e && !strcmp(e, "tc") && f_update_tc_supported(k);
 }
+// TRMF_B200_F_KERNEL=mma1 keeps the first-generation mma.sync kernel (fp32 gather, split in the hot loop: f_update_mma.cuh); the default
+// is the pre-split / ldmatrix kernel of f_update_mma2.cuh.  Both count as F_KERNEL_MMA.
+static bool use_mma2() {
+    const char *e = getenv("TRMF_B200_F_KERNEL");
+    return !(e && !strcmp(e, "mma1"));
+}
 static int f_kernel_choice(int k, const V *X) {
     const char *e = getenv("TRMF_B200_F_KERNEL");
     if (getenv("TRMF_B200_GENERIC_F") || (e && !strcmp(e, "generic"))) return F_KERNEL_GENERIC;
@@ -822,7 +832,8 @@ static int f_kernel_choice(int k, const V *X) {
 // scratch of the mma Gram kernel: the column-scaled factor copy and its inverse scales
 static int mma_scratch(S *s) {
     if (s->Xs) return 0;
-    if (dev_alloc(&s->Xs, std::max(Tcap(s), s->n) * (size_t)s->k) || dev_alloc(&s->invs, 128) || dev_alloc(&s->ysc, 2) || dev_alloc(&s->frow, Tcap(s))) return 1;
+    // (rows of the pre-split fp16 copy are padded to 8 columns per split part: 8 * ceil(k / 8) floats' worth of bytes)
+    if (dev_alloc(&s->Xs, std::max(Tcap(s), s->n) * (size_t)(8 * ((s->k + 7) / 8))) || dev_alloc(&s->invs, 128) || dev_alloc(&s->ysc, 2) || dev_alloc(&s->frow, Tcap(s))) return 1;
     return 0;
 }
 
@@ -1072,8 +1083,28 @@ static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd, const int *gat
 // (TRMF_B200_INLINE_SOLVE) gives bit-identical factors.
 static int mma_f_range(S *s, size_t j0, size_t j1, bool rescale) {
     const int k = s->k;
+    const bool m2 = use_mma2() && !use_tc(k);
+    if (m2) {
+        // weights as fp16 pairs: once per Y (valh_ok), or per slab while the first F-update follows the upload
+        if (s->valh_cap < s->nnz) {
+            dev_free(s->valh);
+            s->valh = nullptr;
+            s->valh_cap = 0;
+            s->valh_ok = false;
+            if (dev_alloc(&s->valh, std::max<size_t>(s->nnz, 1))) return 1;
+            s->valh_cap = std::max<size_t>(s->nnz, 1);
+        }
+        if (!s->valh_ok) {
+            if (f_update_mma2_split_y(s->stream, s->num_sms, s->val, s->col_ptr + j0, (uint32_t)(j1 - j0), s->valh, s->ysc, s->queue + 300, &s->launches))
+                return fail("weight split launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            s->valh_ok = j0 == 0 && j1 == s->n;
+        }
+    }
     if (getenv("TRMF_B200_INLINE_SOLVE")) {
-        if (f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+        if (m2 ? f_update_mma2_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, reinterpret_cast<const V *>(s->valh), s->W, s->T,
+                                                      s->Xs, s->invs, s->H + j0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(j1 - j0), s->queue,
+                                                      &s->launches, nullptr, 0, nullptr, rescale, s->ysc)
+               : f_update_mma_launch<fm::MODE_SOLVE>(s->stream, s->num_sms, s->col_ptr + j0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
                                                 s->H + j0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(j1 - j0), s->queue,
                                                 &s->launches, nullptr, 0, nullptr, rescale))
             return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1096,9 +1127,12 @@ static int mma_f_range(S *s, size_t j0, size_t j1, bool rescale) {
                 return fail("f_update_tc launch failed: %s", cudaGetErrorString(cudaGetLastError()));
             continue;
         }
-        if (f_update_mma_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
+        if ((m2 ? f_update_mma2_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, reinterpret_cast<const V *>(s->valh), s->W,
+                                                       s->T, s->Xs, s->invs, s->H + b0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(b1 - b0),
+                                                       s->queue, &s->launches, nullptr, 0, s->sys, rescale && b0 == j0, s->ysc)
+                : f_update_mma_launch<fm::MODE_DEFER>(s->stream, s->num_sms, s->col_ptr + b0, s->row_idx, s->val, s->W, s->T, s->Xs, s->invs,
                                                 s->H + b0 * (size_t)k, (V *)nullptr, k, s->lambdaI, (uint32_t)(b1 - b0), s->queue,
-                                                &s->launches, nullptr, 0, s->sys, rescale && b0 == j0) ||
+                                                &s->launches, nullptr, 0, s->sys, rescale && b0 == j0)) ||
             f_update_mma_solve(s->stream, s->num_sms, s->col_ptr + b0, s->sys, s->H + b0 * (size_t)k, k, s->lambdaI, (uint32_t)(b1 - b0),
                                &s->launches))
             return fail("f_update_mma launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1219,10 +1253,14 @@ extern "C" int trmf_b200_x_update(S *s) {
                         rc = f_update_tc_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
                                                                one ? s->g : s->part_tk, s->Gt, s->k, (uint32_t)s->T, s->queue, s->ysc, &s->launches,
                                                                s->W, one ? 1 : 0, s->frow);
+                    else if (use_mma2())
+                        rc = f_update_mma2_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
+                                                                 one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
+                                                                 s->W, one ? 1 : 0, s->frow);
                     else
-                    rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
-                                                            one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
-                                                            s->W, one ? 1 : 0, s->frow);
+                        rc = f_update_mma_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
+                                                                one ? s->g : s->part_tk, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches,
+                                                                s->W, one ? 1 : 0, s->frow);
                     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev5, s->stream));
                     s->xg_timed = s->timing;
                     if (!rc) {
@@ -1234,8 +1272,11 @@ extern "C" int trmf_b200_x_update(S *s) {
                         }
                     }
                 } else if (!rc) {
-                    rc = f_update_mma_launch<fm::MODE_STORE>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs,
-                                                             s->invs, s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches);
+                    rc = use_mma2() && !use_tc(s->k)
+                             ? f_update_mma2_launch<fm::MODE_STORE>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs,
+                                                                    s->invs, s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches)
+                             : f_update_mma_launch<fm::MODE_STORE>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs,
+                                                                   s->invs, s->bt, s->Gt, s->k, 0.0, (uint32_t)s->T, s->queue, &s->launches);
                 }
             } else {
                 rc = f_update_tiled_launch<false>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->bt, s->Gt, s->k, 0.0,
