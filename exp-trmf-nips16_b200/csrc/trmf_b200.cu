@@ -25,6 +25,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <memory>
 #include <mutex>
 #include <thread>
 #include <ctime>
@@ -79,6 +80,8 @@ struct trmf_b200_session {
     bool slabs_pending = false;          // the F-update has not consumed the slab events yet
     bool csr_deferred = false;           // the device transpose has not been issued yet
     uint32_t *pack_buf = nullptr;        // pinned staging of the host-packed index bitmap (back to the pool at destroy)
+    uint32_t *bm_dev = nullptr;          // host-packed ingest: the bitmaps in HBM until the first consumer has expanded them
+    uint32_t bm_words = 0;
     size_t pack_bytes = 0;
 
     size_t T = 0, n = 0, nnz = 0;
@@ -293,41 +296,135 @@ __attribute__((target("avx2"))) static void pack_series_avx2(const uint32_t *r, 
     pack_series_scalar(r + i, cnt - i, w);
 }
 #endif
-// Returns false when some series' row indices are not strictly ascending (unsorted arrays or duplicate entries are legal input for
-// the reference's core, which never looks at their order): a bitmap cannot carry those, the caller uploads plain indices instead.
-static bool pack_bitmap_host(const uint64_t *col_ptr, const uint32_t *row_idx, size_t n, uint32_t words, uint64_t rows, uint32_t *out) {
+// TRMF_B200_TRACE: host wall-clock marks inside a host-buffer call (stderr), relative to the first mark
+static void trace_pt(const char *what) {
+    static const bool on = getenv("TRMF_B200_TRACE") != nullptr;
+    if (!on) return;
+    static double t0 = 0;
+    struct timespec tw;
+    clock_gettime(CLOCK_MONOTONIC, &tw);
+    const double t = tw.tv_sec * 1e3 + tw.tv_nsec * 1e-6;
+    if (!strcmp(what, "begin")) t0 = t;
+    fprintf(stderr, "[trmf-b200 trace] %8.3f ms  %s\n", t - t0, what);
+}
+// Branch-free packing at any density: one output word (32 rows) at a time.  The entries of word w are a prefix of what is left of
+// the (ascending) list, at most 32 of them: four 8-lane compares find and count them, a variable shift turns them into bits.
+// No data-dependent branch, so 10 % randomly missing rows cost nothing in mispredictions (a scan for the gaps between runs of
+// consecutive rows paid ~1 per 8 entries and ran at half the speed: profiles/r02_packbench.txt).  0.60 ns per entry and thread on
+// the B200 box's host, 0.71 for round 2's first packer (OR of 8 entries per step, pack_series_avx2).
+// The caller has checked that the indices ascend strictly; `r` must be readable up to r[cnt + 31] (see pack_one_series).
+#if defined(__x86_64__)
+__attribute__((target("avx2,popcnt"))) static void pack_series_words(const uint32_t *r, size_t cnt, uint32_t *w, uint32_t words) {
+    const __m256i one = _mm256_set1_epi32(1), m31 = _mm256_set1_epi32(31);
+    const __m256i lane = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    size_t p = 0;
+    for (uint32_t wi = 0; wi < words && p < cnt; ++wi) {
+        const __m256i wv = _mm256_set1_epi32((int)wi);
+        const long long left = (long long)(cnt - p);
+        const __m256i leftv = _mm256_set1_epi32((int)(left > 64 ? 64 : left));
+        __m256i acc = _mm256_setzero_si256();
+        unsigned taken = 0;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const __m256i idx = _mm256_loadu_si256((const __m256i *)(r + p + 8 * v));
+            const __m256i in = _mm256_and_si256(_mm256_cmpeq_epi32(_mm256_srli_epi32(idx, 5), wv),
+                                                _mm256_cmpgt_epi32(leftv, _mm256_add_epi32(lane, _mm256_set1_epi32(8 * v))));
+            acc = _mm256_or_si256(acc, _mm256_and_si256(_mm256_sllv_epi32(one, _mm256_and_si256(idx, m31)), in));
+            taken += (unsigned)__builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(in)));
+        }
+        w[wi] = pack_hor_avx2(acc);
+        p += taken;
+    }
+}
+// strictly ascending?  (signed compares: the caller guarantees indices below 2^31)
+__attribute__((target("avx2"))) static bool ascending_avx2(const uint32_t *r, size_t cnt) {
+    __m256i ok = _mm256_set1_epi32(-1);
+    size_t i = 0;
+    for (; i + 9 <= cnt; i += 8)
+        ok = _mm256_and_si256(ok, _mm256_cmpgt_epi32(_mm256_loadu_si256((const __m256i *)(r + i + 1)), _mm256_loadu_si256((const __m256i *)(r + i))));
+    unsigned good = _mm256_movemask_ps(_mm256_castsi256_ps(ok)) == 0xff;
+    for (; i + 1 < cnt; ++i) good &= (unsigned)(r[i] < r[i + 1]);
+    return good != 0;
+}
+#endif
+// Bitmap of one series (words = ceil(rows / 32), zeroed here).  Returns false when the row indices are not strictly ascending
+// or reach past `rows` (unsorted arrays or duplicate entries are legal input for the reference's core, which never looks at
+// their order): a bitmap cannot carry those, the caller uploads plain indices instead.
+// `tail_ok`: r[cnt .. cnt + 31] may be read (the series is not among the last of the index array).  algo: 0 = word-wise,
+// 2 = OR per 8 entries (TRMF_B200_PACK_ALGO=or8).
+static bool pack_one_series(const uint32_t *r, size_t cnt, uint32_t *w, uint32_t words, uint64_t rows, bool avx2, bool tail_ok, int algo) {
+    memset(w, 0, (size_t)words * sizeof(uint32_t));
+    if (cnt == 0) return true;
+    if ((uint64_t)r[cnt - 1] >= rows) return false;
+#if defined(__x86_64__)
+    if (avx2 && algo == 0 && tail_ok && rows < (1ull << 31)) {
+        if (!ascending_avx2(r, cnt)) return false;
+        pack_series_words(r, cnt, w, words);
+        return true;
+    }
+#endif
+    unsigned ok = 1;
+    for (size_t i = 0; i + 1 < cnt; ++i) ok &= (unsigned)(r[i] < r[i + 1]);
+    if (!ok) return false;
+#if defined(__x86_64__)
+    if (avx2) { pack_series_avx2(r, cnt, w); return true; }
+#endif
+    pack_series_scalar(r, cnt, w);
+    return true;
+}
+// The index bitmaps of all series, packed by the host cores IN SLAB ORDER while the calling thread waits for slab after slab and
+// hands each to `slab_done(b)` (which enqueues its copies): the first F-update launch only waits for the first slab's bitmap and
+// values, and the copy engine never idles behind the packing.  slab_j = series bounds of the slabs.  Returns false when some
+// series cannot be carried by a bitmap (slab_done may already have been called for earlier slabs) or slab_done failed (*rc = 1).
+template <class F>
+static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, const std::vector<size_t> &slab_j, uint32_t words,
+                              uint64_t rows, uint32_t *out, F slab_done, int *rc) {
     unsigned nt = std::thread::hardware_concurrency();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= (unsigned)std::max(1, atoi(e));   // one process per GPU: share the host cores
     if (const char *e = getenv("TRMF_B200_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    nt = std::max(1u, std::min(nt, 32u));
-    void (*pack)(const uint32_t *, size_t, uint32_t *) = pack_series_scalar;
+    nt = std::max(2u, std::min(nt, 32u));      // (nt - 1 packers + the calling thread)
+    bool avx2 = false;
 #if defined(__x86_64__)
-    if (__builtin_cpu_supports("avx2") && !getenv("TRMF_B200_PACK_SCALAR")) pack = pack_series_avx2;
+    avx2 = __builtin_cpu_supports("avx2") && !getenv("TRMF_B200_PACK_SCALAR");
 #endif
+    int algo = 0;
+    if (const char *e = getenv("TRMF_B200_PACK_ALGO")) algo = !strcmp(e, "or8") ? 2 : 0;
+    const uint64_t nnz_all = col_ptr[slab_j.back()];
+    const size_t nsl = slab_j.size() - 1, chunk = 16;
+    struct Chunk { size_t j0, j1, b; };
+    std::vector<Chunk> chunks;
+    for (size_t b = 0; b < nsl; ++b)
+        for (size_t j = slab_j[b]; j < slab_j[b + 1]; j += chunk) chunks.push_back({j, std::min(slab_j[b + 1], j + chunk), b});
+    std::unique_ptr<std::atomic<size_t>[]> done(new std::atomic<size_t>[nsl]);
+    for (size_t b = 0; b < nsl; ++b) done[b].store(0);
     std::atomic<size_t> next(0);
     std::atomic<bool> bad(false);
-    const size_t chunk = 32;
     auto work = [&]() {
         for (;;) {
-            const size_t j0 = next.fetch_add(chunk);
-            if (j0 >= n || bad.load(std::memory_order_relaxed)) return;
-            const size_t j1 = std::min(n, j0 + chunk);
-            for (size_t j = j0; j < j1; ++j) {
-                uint32_t *w = out + j * (size_t)words;
-                memset(w, 0, (size_t)words * sizeof(uint32_t));
-                const uint32_t *r = row_idx + col_ptr[j];
-                const size_t cnt = (size_t)(col_ptr[j + 1] - col_ptr[j]);
-                unsigned ok = 1;
-                for (size_t i = 0; i + 1 < cnt; ++i) ok &= (unsigned)(r[i] < r[i + 1]);
-                if (cnt && (uint64_t)r[cnt - 1] >= rows) ok = 0;
-                if (!ok) { bad.store(true, std::memory_order_relaxed); return; }
-                pack(r, cnt, w);
-            }
+            const size_t c = next.fetch_add(1);
+            if (c >= chunks.size() || bad.load(std::memory_order_relaxed)) return;
+            for (size_t j = chunks[c].j0; j < chunks[c].j1; ++j)
+                if (!pack_one_series(row_idx + col_ptr[j], (size_t)(col_ptr[j + 1] - col_ptr[j]), out + j * (size_t)words, words, rows, avx2,
+                                     col_ptr[j + 1] + 32 <= nnz_all, algo)) {
+                    bad.store(true);
+                    return;
+                }
+            done[chunks[c].b].fetch_add(chunks[c].j1 - chunks[c].j0, std::memory_order_release);
         }
     };
     std::vector<std::thread> th;
     for (unsigned t = 1; t < nt; ++t) th.emplace_back(work);
-    work();
+    *rc = 0;
+    for (size_t b = 0; b < nsl && !*rc; ++b) {
+        const size_t want = slab_j[b + 1] - slab_j[b];
+        while (done[b].load(std::memory_order_acquire) < want && !bad.load(std::memory_order_relaxed)) {
+#if defined(__x86_64__)
+            _mm_pause();
+#endif
+        }
+        if (bad.load()) break;
+        if (slab_done(b)) { *rc = 1; bad.store(true); }
+    }
     for (auto &t : th) t.join();
     return !bad.load();
 }
@@ -429,7 +526,7 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
-    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys); dev_free(s->valh);
+    dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys); dev_free(s->valh); dev_free(s->bm_dev);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -497,7 +594,9 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     } else {
         return fail("unsupported PyMatrix type %d for Y", Y->type);
     }
+    trace_pt("create: begin common init");
     if (session_common_init(s)) return 1;
+    trace_pt("create: common init done");
     // factors first: the H2D engine serves copies in submission order, and the F-update must not queue
     // behind the side-stream upload of the by-time CSR
     s->own_factors = true;
@@ -578,40 +677,40 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                 return 0;
             };
             const size_t nsl = s->slab_j.size() - 1;
-            // host-packed indices: 5/8 of the value slabs go out, the host cores pack meanwhile, the bitmaps follow on the same copy
-            // stream (so they never queue behind ALL the values) and then the rest of the values.  (Measured alternative,
-            // TRMF_B200_PACK_ORDER=aux: every value slab first and the bitmaps on a stream of their own -- they still wait for the
-            // one host-to-device copy engine: 20.1 against 17.7 ms end to end at C2.)
-            const bool split = host_pack && !(getenv("TRMF_B200_PACK_ORDER") && !strcmp(getenv("TRMF_B200_PACK_ORDER"), "aux"));
-            const size_t first = split ? std::min<size_t>(nsl, (nsl * 5 + 4) / 8) : nsl;
-            for (size_t b = 0; b < first; ++b) if (issue_slab(b)) return 1;
-            if (host_pack) {
+            trace_pt("create: allocations done, issuing slabs");
+            if (!host_pack) {
+                for (size_t b = 0; b < nsl; ++b) if (issue_slab(b)) return 1;
+            } else {
+                // host-packed indices, slab by slab: the host cores pack the bitmaps of slab b while the copy engine is busy with
+                // slab b-1; each slab's bitmap goes out right in front of its values, and the F-update of slab b expands the bitmap
+                // on the device as soon as both have landed (trmf_b200_f_update / wait_slabs).  (Round-2 history: all bitmaps
+                // packed first = the F-update started 6 ms into the call and the copy engine idled for 1 ms: 17.5 ms end to end.)
                 const size_t bytes = (size_t)s->n * bm_words * sizeof(uint32_t);
                 s->pack_buf = bitmap_buf_get(bytes, &s->pack_bytes);
                 if (!s->pack_buf) return fail("cannot allocate %zu bytes of pinned memory for the index bitmaps", bytes);
-                if (dev_alloc(&bm_dev, (size_t)s->n * bm_words)) return 1;
-                cudaStream_t bst = s->copy_stream;
-                if (!split) {
-                    CUDA_TRY(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
-                    bst = s->aux_stream;
-                }
+                if (dev_alloc(&s->bm_dev, (size_t)s->n * bm_words)) return 1;
+                s->bm_words = bm_words;
                 CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));             // (bm_dev's allocation is ordered on s->stream)
-                CUDA_TRY(cudaStreamWaitEvent(bst, s->csr_ready, 0));
-                if (pack_bitmap_host(Y->col_ptr, Y->row_idx, s->n, bm_words, s->T, s->pack_buf)) {
-                    CUDA_TRY(cudaMemcpyAsync(bm_dev, s->pack_buf, bytes, cudaMemcpyHostToDevice, bst));
-                    CUDA_TRY(cudaEventRecord(s->csr_ready, bst));
-                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
-                    bitmap_expand_kernel<<<(unsigned)(s->num_sms * 8), 256, 0, s->stream>>>(s->col_ptr, bm_dev, s->n, s->T, bm_words, s->row_idx);
-                    s->launches++;
-                    CUDA_TRY(cudaGetLastError());
-                } else {
-                    // unsorted or duplicate indices: the whole row_idx array goes over as it is, before anything reads it
-                    CUDA_TRY(cudaMemcpyAsync(s->row_idx, Y->row_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, bst));
-                    CUDA_TRY(cudaEventRecord(s->csr_ready, bst));
-                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->csr_ready, 0));
+                CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
+                int rc = 0;
+                auto slab_packed = [&](size_t b) -> int {
+                    const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
+                    CUDA_TRY(cudaMemcpyAsync(s->bm_dev + j0 * (size_t)bm_words, s->pack_buf + j0 * (size_t)bm_words,
+                                             (j1 - j0) * (size_t)bm_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                    return issue_slab(b);
+                };
+                const bool packed = pack_bitmap_slabs(Y->col_ptr, Y->row_idx, s->slab_j, bm_words, s->T, s->pack_buf, slab_packed, &rc);
+                trace_pt("create: host pack done, every slab enqueued");
+                if (rc) return 1;
+                if (!packed) {
+                    // unsorted or duplicate indices: the whole row_idx array goes over as it is, then whatever slabs are still
+                    // missing; every slab event is (re-)recorded behind it, so nothing reads row_idx before it is complete
+                    dev_free(s->bm_dev);
+                    s->bm_dev = nullptr;
+                    CUDA_TRY(cudaMemcpyAsync(s->row_idx, Y->row_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                    for (size_t b = s->slab_ev.size(); b < nsl; ++b) if (issue_slab(b)) return 1;
+                    for (cudaEvent_t ev : s->slab_ev) CUDA_TRY(cudaEventRecord(ev, s->copy_stream));
                 }
-                dev_free(bm_dev);
-                for (size_t b = first; b < nsl; ++b) if (issue_slab(b)) return 1;
             }
             s->slabs_pending = true;
         }
@@ -720,6 +819,23 @@ extern "C" int trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, cons
     return rc;
 }
 
+// the host half of the packed ingest on its own (no device involved): what c_trmf_train does to plain row indices of a mostly-observed
+// matrix before they cross PCIe.  Returns 0 = packed, 1 = declined (indices not strictly ascending within a series, or >= T).
+extern "C" int trmf_b200_pack_bitmap_host(uint64_t T, uint64_t n, const uint64_t *col_ptr, const uint32_t *row_idx, uint32_t *bitmap) {
+    g_last_error.clear();
+    if (T >= (1ull << 32)) return fail("T must fit uint32 indices");
+    // a few slabs, so that the slab-ordered hand-over is exercised too
+    std::vector<size_t> slab_j(1, 0);
+    for (int b = 1; b <= 3; ++b) { const size_t j = (size_t)(n * b / 3); if (j > slab_j.back()) slab_j.push_back(j); }
+    if (slab_j.back() < n) slab_j.push_back((size_t)n);
+    if (slab_j.size() < 2) return 0;
+    int rc = 0;
+    size_t seen = 0;
+    const bool ok = pack_bitmap_slabs(col_ptr, row_idx, slab_j, (uint32_t)((T + 31) / 32), T, bitmap, [&](size_t b) { seen += b == seen; return 0; }, &rc);
+    if (ok && seen != slab_j.size() - 1) return fail("slabs were not handed over in order");
+    return ok ? 0 : 1;
+}
+
 extern "C" int trmf_b200_bitmap_expand(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *bitmap,
                                        uint32_t *row_idx, int32_t device) {
     g_last_error.clear();
@@ -752,12 +868,13 @@ extern "C" int trmf_b200_set_params(S *s, double lambdaI, double lambdaAR, doubl
     return 0;
 }
 
+static int wait_slabs(S *s);
 extern "C" int trmf_b200_set_stream(S *s, void *cuda_stream) {
     CUDA_TRY(cudaSetDevice(s->device));
     if (s->copy_stream) CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
     if (s->aux_stream) CUDA_TRY(cudaStreamSynchronize(s->aux_stream));
     s->csr_pending = false;
-    s->slabs_pending = false;   // (everything has landed; a deferred CSR build simply runs on the new stream)
+    if (wait_slabs(s)) return 1;   // (everything has landed: expands host-packed bitmaps; a deferred CSR build simply runs on the new stream)
     CUDA_TRY(cudaStreamSynchronize(s->stream));
     if (s->own_stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
     s->stream = (cudaStream_t)cuda_stream;
@@ -772,9 +889,23 @@ extern "C" int trmf_b200_sync(S *s) {
 }
 
 // the whole by-series CSC has landed (a consumer other than the slab-wise F-update calls this)
+// host-packed ingest: row indices of the series [j0, j1) out of their bitmaps (the slab's copies are already waited for)
+static int expand_slab_bitmaps(S *s, size_t j0, size_t j1) {
+    if (!s->bm_dev || j1 <= j0) return 0;
+    const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)s->num_sms * 8, (j1 - j0 + 7) / 8));
+    bitmap_expand_kernel<<<grid, 256, 0, s->stream>>>(s->col_ptr + j0, s->bm_dev + j0 * (size_t)s->bm_words, j1 - j0, s->T, s->bm_words, s->row_idx);
+    s->launches++;
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
 static int wait_slabs(S *s) {
     if (!s->slabs_pending) return 0;
     for (cudaEvent_t e : s->slab_ev) CUDA_TRY(cudaStreamWaitEvent(s->stream, e, 0));
+    if (s->bm_dev) {
+        if (expand_slab_bitmaps(s, 0, s->n)) return 1;
+        dev_free(s->bm_dev);
+        s->bm_dev = nullptr;
+    }
     s->slabs_pending = false;
     return 0;
 }
@@ -1158,8 +1289,10 @@ extern "C" int trmf_b200_f_update(S *s) {
                 // first F-update of a host-buffer session: one launch per series slab, each as soon as its slab has landed
                 for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
                     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
+                    if (expand_slab_bitmaps(s, s->slab_j[b], s->slab_j[b + 1])) return 1;
                     if (mma_f_range(s, s->slab_j[b], s->slab_j[b + 1], b == 0)) return 1;
                 }
+                if (s->bm_dev) { dev_free(s->bm_dev); s->bm_dev = nullptr; }
                 s->slabs_pending = false;
             } else if (mma_f_range(s, 0, s->n, true)) return 1;
         } else if (fk == F_KERNEL_FFMA) {
@@ -1447,6 +1580,8 @@ extern "C" int trmf_b200_train(S *s, int32_t max_iter, int32_t period_W, int32_t
         double nv = 0;
         if (iter % period_H == 0) {
             if (trmf_b200_f_update(s)) return 1;
+            trace_pt("train: F-update enqueued");
+            if (getenv("TRMF_B200_TRACE_SYNC")) { cudaStreamSynchronize(s->stream); trace_pt("train: F-update finished on the device"); }
             if (verbose) {
                 if (dot(s, s->H, s->H, nk, SC_TMP) || dist_allreduce_f64(s, s->scal + SC_TMP, 1) || read_scalars(s)) return 1;
                 fprintf(stderr, ">> iter %d F %g\n", iter, s->h_scal[SC_TMP]);
@@ -1454,6 +1589,7 @@ extern "C" int trmf_b200_train(S *s, int32_t max_iter, int32_t period_W, int32_t
         }
         if (iter % period_W == 0) {
             if (trmf_b200_x_update(s)) return 1;
+            trace_pt("train: X-update returned (its scalars were read back)");
             if (verbose >= 2) {
                 fprintf(stdout, "iter %2d act %5.3e pre %5.3e delta %5.3e f %5.3e |g| %5.3e CG %3d |g| %5.3e\n", 1, s->st_actred,
                         s->st_prered, s->st_delta, s->st_f, s->st_gnorm, (int)s->st_cg, s->st_rnorm);
@@ -1610,6 +1746,7 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
         return tw.tv_sec * 1e3 + tw.tv_nsec * 1e-6;
     };
     const double t0 = now_ms();
+    trace_pt("begin");
     // device: TRMF_B200_DEVICE if set, else the calling thread's current CUDA device (e.g. torch.cuda.set_device);
     // the caller's current device is put back before returning
     int prev_dev = 0, dev = 0;
@@ -1625,7 +1762,9 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     double t1 = now_ms();
     if (trace) { cudaStreamSynchronize(s->stream); t1 = now_ms(); }
     trmf_b200_set_params(s, lambdaI, lambdaAR, lambdaLag);
+    trace_pt("train: begin");
     const int rc = trmf_b200_train(s, max_iter, period_W, period_H, period_Lag, verbose);
+    trace_pt("train: returned");
     double t2 = now_ms();
     if (trace) { cudaStreamSynchronize(s->stream); t2 = now_ms(); }
     if (rc == 0) trmf_b200_download(s, pyW->val, pyH->val, pylag_val->val);

@@ -189,6 +189,13 @@ int  trmf_b200_copy_to_host(void *dst_host, const void *src_device, uint64_t byt
 int  trmf_b200_csr_from_csc(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *row_idx,
                             const void *val, uint64_t *row_ptr, uint32_t *col_idx, void *val_t, int32_t device);
 
+/* Ingest primitive, host half: the per-series bitmaps (n x ceil(T / 32) uint32 words, bit (i & 31) of word [j][i >> 5] set iff
+ * (i, j) is stored) that c_trmf_train packs out of plain row indices on the host cores before they cross PCIe.  No device
+ * involved.  Returns 0 = packed, 1 = declined (row indices of some series not strictly ascending, or >= T: the reference's core
+ * accepts those, a bitmap cannot carry them, and c_trmf_train then uploads the plain indices).  Replaces nothing in the
+ * reference (rf_util.py:88-98 hands both index arrays over as they are). */
+int  trmf_b200_pack_bitmap_host(uint64_t T, uint64_t n, const uint64_t *col_ptr, const uint32_t *row_idx, uint32_t *bitmap);
+
 /* Ingest primitive: the row_idx array (uint32[nnz], ascending within every series) of a TRMF_SPARSE_BITMAP matrix,
  * expanded on the device; host arrays in, host array out (parity tests of the packed ingest). */
 int  trmf_b200_bitmap_expand(uint64_t T, uint64_t n, uint64_t nnz, const uint64_t *col_ptr, const uint32_t *bitmap,

@@ -229,3 +229,48 @@ def test_coo_pymatrix_keeps_duplicate_entries_like_the_reference():
         assert np.array_equal(got, want)
     with pytest.raises(ValueError):
         PyMatrix(coo, np.float64, pack=True)
+
+
+def test_host_packing_of_row_indices_matches_the_numpy_mask():
+    """csrc/trmf_b200.cu:pack_bitmap_slabs (gap method for series that are dense inside their span, word-wise OR otherwise,
+    packed slab by slab by worker threads): same words as trmf.rf_util.pack_bitmap; unsorted / duplicate / out-of-range
+    indices are declined (the caller then uploads plain indices).  No device involved."""
+    import ctypes
+    import scipy.sparse as sps
+    from trmf.rf_util import pack_bitmap
+    lib = ctypes.CDLL(os.path.join(CORELIB, "trmf_float32.so"))
+    fn = lib.trmf_b200_pack_bitmap_host
+    fn.argtypes = [ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    fn.restype = ctypes.c_int
+    rng = np.random.RandomState(5)
+
+    def run(T, col_ptr, row_idx):
+        n = len(col_ptr) - 1
+        out = np.full(n * ((T + 31) // 32), 0xdeadbeef, dtype=np.uint32)
+        rc = fn(T, n, col_ptr.ctypes.data, row_idx.ctypes.data, out.ctypes.data)
+        return rc, out
+
+    for T, n, d in [(300, 200, 0.9), (1000, 64, 0.97), (33, 4, 0.9), (32, 3, 1.0), (1, 1, 1.0), (64, 64, 0.0), (70001, 5, 0.5),
+                    (5000, 40, 0.05), (4099, 37, 0.6), (257, 100, 0.995)]:
+        m = sps.random(T, n, density=d, format="csc", random_state=rng)
+        m.sort_indices()
+        col_ptr, row_idx = m.indptr.astype(np.uint64), m.indices.astype(np.uint32)
+        buf = row_idx if len(row_idx) else np.zeros(1, dtype=np.uint32)   # (a valid pointer for the empty matrix)
+        rc, out = run(T, col_ptr, buf)
+        assert rc == 0
+        assert np.array_equal(out, pack_bitmap(col_ptr, row_idx, T)), (T, n, d)
+    # long gaps that span several words, runs that end exactly on word boundaries, a single entry, first / last row only
+    T = 1000
+    series = [np.arange(0, 32), np.arange(31, 65), np.r_[np.arange(0, 10), np.arange(500, 520), 999], np.array([999]), np.array([0]),
+              np.r_[0, 999], np.arange(0, 1000), np.arange(1, 999, 2), np.r_[np.arange(0, 64), np.arange(96, 128)]]
+    col_ptr = np.r_[0, np.cumsum([len(x) for x in series])].astype(np.uint64)
+    row_idx = np.concatenate(series).astype(np.uint32)
+    rc, out = run(T, col_ptr, row_idx)
+    assert rc == 0 and np.array_equal(out, pack_bitmap(col_ptr, row_idx, T))
+    # declined: a swapped pair inside a dense series, a duplicate, an index >= T
+    base = np.arange(0, 400, dtype=np.uint32)
+    for bad in (np.r_[base[:100], base[101], base[100], base[102:]], np.r_[base[:50], base[49:]], np.r_[base[:-1], T + 5],
+                np.r_[base[200:], base[:200]]):
+        cp = np.array([0, len(bad)], dtype=np.uint64)
+        rc, _ = run(T, cp, np.ascontiguousarray(bad, dtype=np.uint32))
+        assert rc == 1
