@@ -1,0 +1,241 @@
+// complement.cuh -- the sparse F-update and the X-update's Gram build for a MOSTLY OBSERVED Y (fp32 build): work over the missing
+// cells instead of the observed ones.
+//
+// Same results as l2r_ls_pY_IX_chol::solve (reference trmf.cpp:369-397) and arr_ls_pY_IX::fun / ::grad (trmf.cpp:231-267), which walk
+// the observed set Omega_r of every row r (r = a series for the F-update, a time stamp for the X-update; X = the other factor):
+//
+//      Gram_r  = sum_{e in Omega_r} x_e x_e^T          = X^T X  -  sum_{e NOT in Omega_r} x_e x_e^T
+//      rhs_r   = sum_{e in Omega_r} y_re x_e            = (Y0 X)_r          with Y0 = Y zero-filled at the missing cells
+//
+// BASELINE configs[1] (C2) and the traffic shape (C3) observe 90 % of their cells: the complement has a NINTH of the entries, so the
+// gather-bound Gram kernel (f_update_mma2.cuh, MODE_GONLY) runs over 1e7 instead of 9e7 entries, and what needs the Y values collapses
+// into one tall-skinny dense product that reads Y0 (T x n floats) once.  It is also the more accurate formulation: X^T X is summed in
+// fp64 from fp32 products and the split-fp16 tensor-core part (7e-8 relative) only carries the tenth of the Gram that is subtracted.
+//
+// For the X-update the same Gram (stored fp32 for the CG mat-vecs) also gives the loss gradient and value at the current point w_r
+// while it is still in fp64:   sum_{e in Omega_r} z_e x_e = Gram_r w_r - rhs_r,   sum z_e^2 = w_r^T (Gram_r w_r - 2 rhs_r) + sum y^2.
+//
+// Used when nnz >= 0.6 T n (TRMF_B200_COMPLEMENT=0 / 1 pins it); rows without any observation are handled like in the walks (F row
+// untouched, zero Gram).  Everything is deterministic (fixed summation orders).
+#pragma once
+#include "common.cuh"
+#include "dense.cuh"
+#include "ingest.cuh"
+// (-DValueType=... is a macro; CUB uses that word as a template parameter name)
+#pragma push_macro("ValueType")
+#undef ValueType
+#include <cub/device/device_scan.cuh>
+#pragma pop_macro("ValueType")
+
+#ifdef TRMF_F32
+namespace cm {
+
+// ---- the missing cells of every row as an index list (complement of a CSR/CSC half with ascending indices) ----
+__global__ void count_missing_kernel(const uint64_t *__restrict__ ptr, uint64_t rows, uint64_t dim, uint64_t *__restrict__ cnt) {
+    for (uint64_t r = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; r <= rows; r += (uint64_t)gridDim.x * blockDim.x)
+        cnt[r] = r < rows ? dim - (ptr[r + 1] - ptr[r]) : 0;
+}
+// bitmap[r][w] = ~(bits of the observed indices): one warp per row
+__global__ void missing_bitmap_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, uint64_t rows, uint32_t words,
+                                      uint32_t *__restrict__ bitmap) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r < rows; r += nwarps) {
+        uint32_t *bm = bitmap + r * (uint64_t)words;
+        for (uint32_t w = lane; w < words; w += 32) bm[w] = 0u;
+        __syncwarp();
+        const uint64_t e0 = ptr[r], e1 = ptr[r + 1];
+        for (uint64_t e = e0; e < e1; e += 32) {     // ascending indices: the lanes of one word are neighbours; one atomic per word and step
+            const bool on = e + lane < e1;
+            const uint32_t i = on ? idx[e + lane] : 0xffffffffu;
+            const unsigned grp = __match_any_sync(FULL_MASK, i >> 5);
+            const uint32_t bits = __reduce_or_sync(grp, on ? 1u << (i & 31) : 0u);
+            if (on && lane == __ffs(grp) - 1) atomicOr(bm + (i >> 5), bits);
+        }
+        __syncwarp();
+        for (uint32_t w = lane; w < words; w += 32) bm[w] = ~bm[w];     // (bits past `dim` in the last word are masked by the expansion)
+    }
+}
+
+// Y0[t * n + j] = Y_tj at the observed cells (the buffer is zeroed first); from the by-time CSR, so a row's stores are nearly contiguous
+__global__ void scatter_dense_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col_idx, const float *__restrict__ val_t,
+                                     uint64_t T, uint64_t n, float *__restrict__ Y0) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t t = warp; t < T; t += nwarps) {
+        const uint64_t e0 = row_ptr[t], e1 = row_ptr[t + 1];
+        float *row = Y0 + t * n;
+        for (uint64_t e = e0 + lane; e < e1; e += 32) row[col_idx[e]] = val_t[e];
+    }
+}
+// yy[t] = sum of squares of row t's values (fp64; one warp per row, fixed order)
+__global__ void row_sumsq_kernel(const uint64_t *__restrict__ row_ptr, const float *__restrict__ val_t, uint64_t T, double *__restrict__ yy) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t t = warp; t < T; t += nwarps) {
+        double a = 0.0;
+        for (uint64_t e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) a += (double)val_t[e] * (double)val_t[e];
+        a = warp_sum(a);
+        if (lane == 0) yy[t] = a;
+    }
+}
+
+// ---- tall-skinny product in fp64 ----
+// Cpart[split][m][c] = sum_{kappa in the split's range} A(m, kappa) * B[kappa][c],  A(m, kappa) = A[m * sm + kappa * sk] (one of sm, sk is 1),
+// B row-major (kappa x N), N <= 64; fp32 inputs, DFMA accumulation (B200 issues half as many DFMAs as FFMAs per clock -- and the
+// right-hand sides need it: on an ill-conditioned system a 1e-7 relative error of the right-hand side alone moves the solution by
+// 3e-5, tests/test_complement_gpu.py).  CTA tile: 128 rows x all N columns, 32 kappa per step staged in shared memory as doubles
+// while the next step's values are already in flight in registers; a thread owns 4 rows x ceil(N / 8) columns.  Same split-K /
+// finish scheme as dense.cuh (gemm_finish_kernel sums the splits in order).
+constexpr int GM = 128, GK = 32, GAS = GM + 2;     // (row stride of the A tile in doubles: 16-byte aligned)
+template <int NQ>
+__global__ void __launch_bounds__(256)
+gemm64_partial_kernel(const float *__restrict__ A, size_t sm, size_t sk, const float *__restrict__ B, size_t M, int N, size_t K,
+                      size_t kchunk, double *__restrict__ Cpart) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double (*As)[GAS] = reinterpret_cast<double (*)[GAS]>(smem_raw);                       // [GK][GAS]
+    double (*Bs)[64] = reinterpret_cast<double (*)[64]>(smem_raw + sizeof(double) * GK * GAS);   // [GK][64]
+    const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;     // lane = row group (4 rows), warp = column group
+    const size_t m0 = (size_t)blockIdx.x * GM;
+    const size_t k0 = (size_t)blockIdx.y * kchunk, k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
+    double acc[4][NQ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) acc[i][q] = 0.0;
+    float ra[16], rb[8];       // the next step's share of the A tile (128 x 32 / 256) and of the B tile (32 x 64 / 256)
+    auto fetch = [&](size_t kk) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int p = tid + 256 * u;
+            int kq, mq;
+            if (sk == 1) { kq = p % GK; mq = p / GK; } else { mq = p % GM; kq = p / GM; }
+            const size_t m = m0 + mq, kap = kk + kq;
+            ra[u] = (m < M && kap < k1) ? __ldg(A + m * sm + kap * sk) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int p = tid + 256 * u, c = p & 63, kq = p >> 6;
+            const size_t kap = kk + kq;
+            rb[u] = (c < N && kap < k1) ? __ldg(B + kap * N + c) : 0.f;
+        }
+    };
+    fetch(k0);
+    for (size_t kk = k0; kk < k1; kk += GK) {
+        __syncthreads();          // the previous step's tiles are consumed
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const int p = tid + 256 * u;
+            int kq, mq;
+            if (sk == 1) { kq = p % GK; mq = p / GK; } else { mq = p % GM; kq = p / GM; }
+            As[kq][mq] = (double)ra[u];
+        }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int p = tid + 256 * u; Bs[p >> 6][p & 63] = (double)rb[u]; }
+        __syncthreads();
+        if (kk + GK < k1) fetch(kk + GK);
+#pragma unroll 4
+        for (int kq = 0; kq < GK; ++kq) {
+            const double2 a01 = *reinterpret_cast<const double2 *>(&As[kq][4 * lane]), a23 = *reinterpret_cast<const double2 *>(&As[kq][4 * lane + 2]);
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) {
+                const double b = Bs[kq][cg + 8 * q];
+                acc[0][q] = fma(a01.x, b, acc[0][q]);
+                acc[1][q] = fma(a01.y, b, acc[1][q]);
+                acc[2][q] = fma(a23.x, b, acc[2][q]);
+                acc[3][q] = fma(a23.y, b, acc[3][q]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const size_t m = m0 + 4 * lane + i;
+        if (m < M) {
+            double *dst = Cpart + ((size_t)blockIdx.y * M + m) * N;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) { const int c = cg + 8 * q; if (c < N) dst[c] = acc[i][q]; }
+        }
+    }
+}
+constexpr size_t gemm64_smem = sizeof(double) * ((size_t)GK * GAS + (size_t)GK * 64);
+
+// ---- F-update: (X^T X - Gmiss_j + lambda I) f = rhs_j, one CTA per system at a time (fp64 Cholesky of common.cuh) ----
+// sys[j] = the (K+1) x (K+1) lower-triangle layout MODE_GONLY leaves (only read when the series has missing cells), XtX = K x K fp64
+// (full), rhs = n x K fp64.  A series without any observation keeps its row (trmf.cpp:374).
+template <int K>
+__global__ void __launch_bounds__(128)
+solve_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ XtX,
+             const double *__restrict__ rhs, float *__restrict__ F, double lambda, uint32_t nseries) {
+    constexpr int ld = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A = reinterpret_cast<double *>(smem_raw);
+    double *dinv = A + (size_t)(K + 1) * ld;
+    const int tid = threadIdx.x;
+    for (uint32_t j = blockIdx.x; j < nseries; j += gridDim.x) {
+        if (ptr[j + 1] == ptr[j]) continue;
+        const bool miss = cptr[j + 1] != cptr[j];
+        const double *src = sys + (size_t)j * ((K + 1) * ld);
+        for (int p = tid; p < K * K; p += 128) {
+            const int r = p / K, c = p - r * K;
+            if (c <= r) A[r * ld + c] = XtX[p] - (miss ? src[r * ld + c] : 0.0);
+        }
+        if (tid < K) A[K * ld + tid] = rhs[(size_t)j * K + tid];
+        __syncthreads();
+        if (tid < K) A[tid * ld + tid] += lambda;       // trmf.cpp:393
+        block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, K);   // starts and ends with __syncthreads
+        if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
+        __syncthreads();
+    }
+}
+
+// ---- X-update: Gram_t = H^T H - Gmiss_t -> Gout[t] (fp32, full square); loss gradient and value at the point Wv from the fp64 Gram ----
+// grad row: F[t] (+)= Gram_t w_t - rhs_t;  frow[t] = w_t^T (Gram_t w_t - 2 rhs_t) + yy[t]  (= sum of squared residuals of row t).
+// A time stamp without observations: zero Gram, frow 0, gradient row untouched (gaccum) or zero -- as the walk leaves it.
+template <int K>
+__global__ void __launch_bounds__(128)
+xgram_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ HtH,
+             const double *__restrict__ rhs, const double *__restrict__ yy, const float *__restrict__ Wv, float *__restrict__ F,
+             float *__restrict__ Gout, int gaccum, double *__restrict__ frow, uint32_t nrows) {
+    constexpr int ld = K + 1;
+    __shared__ double G[K * ld];
+    __shared__ double w[K];
+    __shared__ double red[4];
+    const int tid = threadIdx.x;
+    for (uint32_t t = blockIdx.x; t < nrows; t += gridDim.x) {
+        float *Gt = Gout + (size_t)t * K * K;
+        if (ptr[t + 1] == ptr[t]) {
+            for (int p = tid; p < K * K; p += 128) Gt[p] = 0.f;
+            if (tid == 0) frow[t] = 0.0;
+            if (!gaccum && tid < K) F[(size_t)t * K + tid] = 0.f;
+            continue;
+        }
+        const bool miss = cptr[t + 1] != cptr[t];
+        const double *src = sys + (size_t)t * ((K + 1) * ld);
+        for (int p = tid; p < K * K; p += 128) {
+            const int r = p / K, c = p - r * K;
+            const double g = HtH[p] - (miss ? (c <= r ? src[r * ld + c] : src[c * ld + r]) : 0.0);
+            G[r * ld + c] = g;
+            Gt[p] = (float)g;
+        }
+        if (tid < K) w[tid] = (double)Wv[(size_t)t * K + tid];
+        __syncthreads();
+        double part = 0.0;
+        if (tid < K) {
+            double a = 0.0;
+#pragma unroll 8
+            for (int c = 0; c < K; ++c) a += G[tid * ld + c] * w[c];
+            const double r = rhs[(size_t)t * K + tid];
+            float *o = F + (size_t)t * K + tid;
+            *o = gaccum ? (float)((double)*o + (a - r)) : (float)(a - r);
+            part = w[tid] * (a - 2.0 * r);
+        }
+        part = warp_sum(part);
+        if ((tid & 31) == 0) red[tid >> 5] = part;
+        __syncthreads();
+        if (tid == 0) frow[t] = ((red[0] + red[1]) + (red[2] + red[3])) + yy[t];
+        __syncthreads();
+    }
+}
+
+}   // namespace cm
+#endif

@@ -162,7 +162,9 @@ __global__ void colscale_apply_kernel(const float *__restrict__ X, size_t rows, 
 //              off the tensor pipe for the length of a 128-thread Cholesky; with few entries per series (C5: 2 000
 //              at k = 64) that is half of the F-update, while the separate kernel runs 6-16 solves per SM at once.
 // X is the column-scaled factor (colscale_apply_kernel), invs its inverse scales.
-enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3 };
+// MODE_GONLY : (f_update_mma2.cuh only) MODE_DEFER without a right-hand side: the Gram alone goes to sys[j]; used over the COMPLEMENT of
+//              the observed set (complement.cuh), where there are no Y values.
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3, MODE_GONLY = 4 };
 template <int K, int NW, int MINB, int MODE>
 __global__ void __launch_bounds__(NW * 32, MINB)
 f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict__ idx, const float *__restrict__ val,
@@ -575,7 +577,7 @@ static inline bool f_update_mma_supported(int) { return false; }
 static inline size_t f_update_mma_sys_doubles(int) { return 0; }
 static inline int f_update_mma_solve(cudaStream_t, int, const uint64_t *, const double *, V *, int, double, uint32_t, unsigned long long *) { return 1; }
 namespace fm {
-enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3 };
+enum { MODE_SOLVE = 0, MODE_STORE = 1, MODE_GRAD = 2, MODE_DEFER = 3, MODE_GONLY = 4 };
 __global__ void sum_rows_kernel(const double *, size_t, double, double *, unsigned *, double *) {}
 }
 template <int MODE>

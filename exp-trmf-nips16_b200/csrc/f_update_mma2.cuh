@@ -53,8 +53,12 @@ template <int K, int ST = 2> struct Cfg2 {
 
 // Xh[i] = [h1 | h2] of X[i] * s (s = the exact per-column power-of-two scales of colscale_max_kernel: column maximum into
 // [2^14, 2^15)), each half padded with zeros to kp = 8 * ceil(k / 8) columns.  invs[c] = 1 / s_c.
+// Xr (optional, rows x k fp32) = the values the split actually carries, (h1 + h2) / s: exact in fp32, 22 of x's 24 significant bits.
+// Whatever is combined with a Gram of the split factor (complement.cuh) reads THIS copy, so that Gram and right-hand side describe
+// the same (slightly rounded) least-squares problem -- the normal equations forgive a consistent perturbation of the data, not an
+// independent one of the Gram or the right-hand side.
 __global__ void presplit_kernel(const float *__restrict__ X, size_t rows, int k, const unsigned *__restrict__ colmax,
-                                __half *__restrict__ Xh, float *__restrict__ invs) {
+                                __half *__restrict__ Xh, float *__restrict__ invs, float *__restrict__ Xr) {
     extern __shared__ float sc[];
     for (int c = threadIdx.x; c < k; c += blockDim.x) {
         const float m = __uint_as_float(colmax[c]);
@@ -82,6 +86,11 @@ __global__ void presplit_kernel(const float *__restrict__ X, size_t rows, int k,
         __half2 *row = reinterpret_cast<__half2 *>(Xh + i * (size_t)(2 * kp));
         row[c / 2] = h1;
         row[(kp + c) / 2] = h2;
+        if (Xr != nullptr) {
+            const float2 f2 = __half22float2(h2);
+            if (c < k) Xr[i * k + c] = (f1.x + f2.x) / sc[c];
+            if (c + 1 < k) Xr[i * k + c + 1] = (f1.y + f2.y) / sc[c + 1];
+        }
     }
 }
 
@@ -131,8 +140,10 @@ __device__ __noinline__ void issue_ragged_tile(const unsigned gdst_s, const unsi
         const uint32_t row = __shfl_sync(FULL_MASK, nidx, (ge + q * rpr) & 15);
         if (g_on && ge + q * rpr < cnt) cp_async16_s(gdst_s + (unsigned)(q * rpr * us * 16), gsrc + (size_t)row * rowb);
     }
-    if (lane < cnt) cp_async4(ysm + lane, yg + lane);
-    else if (lane < ET) ysm[lane] = 0.f;
+    if (yg != nullptr) {
+        if (lane < cnt) cp_async4(ysm + lane, yg + lane);
+        else if (lane < ET) ysm[lane] = 0.f;
+    }
     for (int p = cnt * us * 4 + lane; p < ET * us * 4; p += 32) rows32[p] = 0u;   // rows past the end read as zero
 }
 
@@ -170,8 +181,9 @@ f_update_mma2_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restric
                      float *__restrict__ Gout, double lambda, uint32_t nseries, unsigned *__restrict__ queue,
                      const float *__restrict__ Wv, int gaccum, double *__restrict__ frow, const float *__restrict__ ysc) {
     typedef Cfg2<K, ST> C;
-    constexpr bool SOLVE = MODE == MODE_SOLVE || MODE == MODE_DEFER, GRAD = MODE == MODE_GRAD, DEFER = MODE == MODE_DEFER;
-    constexpr bool YPRE = SOLVE;       // weights arrive pre-split, one global scale
+    constexpr bool GONLY = MODE == MODE_GONLY;      // Gram only: no weights, no right-hand side
+    constexpr bool SOLVE = MODE == MODE_SOLVE || MODE == MODE_DEFER || GONLY, GRAD = MODE == MODE_GRAD, DEFER = MODE == MODE_DEFER || GONLY;
+    constexpr bool YPRE = SOLVE && !GONLY;          // weights arrive pre-split, one global scale
     constexpr int NC = C::NC, MT = C::MT, NT = C::NT, UR = C::UR, US = C::US, STAGES = C::STAGES;
     constexpr int SB = C::STAGE_B, ld = C::ld, NTH = NW * 32, PW = C::PW, RSTR = C::RSTR, ROWB = C::ROWB;
     constexpr bool ODD = C::ODD;
@@ -289,9 +301,9 @@ f_update_mma2_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restric
                             if (g_on && ((q + 1) * RPR <= ET || ge + q * RPR < ET))
                                 cp_async16_s(gdst_s + (unsigned)(s * SB + q * RPR * US * 16), gsrc + (size_t)row * ROWB);
                         }
-                        if (lane < ET) cp_async4(ys + s * ET + lane, sval + ib + lane);
+                        if (!GONLY && lane < ET) cp_async4(ys + s * ET + lane, sval + ib + lane);
                     } else {
-                        issue_ragged_tile(gdst_s + (unsigned)(s * SB), gsrc, nidx, (int)(nnz - ib), g_on, ge, ys + s * ET, sval + ib,
+                        issue_ragged_tile(gdst_s + (unsigned)(s * SB), gsrc, nidx, (int)(nnz - ib), g_on, ge, ys + s * ET, GONLY ? nullptr : sval + ib,
                                           reinterpret_cast<uint32_t *>(st + s * SB), RPR, NQ, US, ROWB);
                     }
                     ib += NW * ET;
@@ -330,7 +342,9 @@ f_update_mma2_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restric
                     constexpr int s = decltype(sc)::value;
                     uint32_t by[2];      // B fragment of the weights: column 0 = first fp16 part, column 1 = second, rows = the tile's entries
                     float inv_sy = 0.f;
-                    if (YPRE) {
+                    if (GONLY) {
+                        by[0] = by[1] = 0u;
+                    } else if (YPRE) {
                         uint32_t w0, w1, w2, w3;
                         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w0), "=r"(w1) : "r"(yrd_s + (unsigned)(s * ET * 4)) : "memory");
                         asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(w2), "=r"(w3) : "r"(yrd_s + (unsigned)(s * ET * 4 + 32)) : "memory");
@@ -413,6 +427,7 @@ f_update_mma2_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restric
                             for (int q = 0; q < 4; ++q) acc[t][q] += d[q];
                             ++t;
                         }
+                        if (GONLY) continue;
                         float d[4];
                         mma_zero(d, a2, by);
                         mma_acc(d, a1, by);
@@ -535,7 +550,7 @@ static inline int f_update_mma2_launch(cudaStream_t st, int num_sms, const uint6
                                        const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
                                        uint32_t nseries, unsigned *queue, unsigned long long *launches,
                                        const V *Wv = nullptr, int gaccum = 0, double *frow = nullptr, bool rescale = true,
-                                       const float *ysc = nullptr) {
+                                       const float *ysc = nullptr, V *Xr = nullptr) {
     if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (rescale ? 8 + 128 : 1), st) != cudaSuccess) return 1;
     if (rescale) {
         const size_t total = xrows * (size_t)k;
@@ -544,7 +559,7 @@ static inline int f_update_mma2_launch(cudaStream_t st, int num_sms, const uint6
         if (g1 == 0) g1 = 1;
         if ((size_t)g1 * 256 < (size_t)k) g1 = (unsigned)((k + 255) / 256);
         fm::colscale_max_kernel<<<g1, 256, 0, st>>>(X, xrows, k, queue + 8);
-        fm::presplit_kernel<<<g1, 256, sizeof(float) * k, st>>>(X, xrows, k, queue + 8, reinterpret_cast<__half *>(Xs), invs);
+        fm::presplit_kernel<<<g1, 256, sizeof(float) * k, st>>>(X, xrows, k, queue + 8, reinterpret_cast<__half *>(Xs), invs, Xr);
         *launches += 2;
     }
     const bool wide = nseries < (uint32_t)(24 * num_sms);
@@ -582,5 +597,5 @@ static inline int f_update_mma2_split_y(cudaStream_t, int, const V *, const uint
 template <int MODE>
 static inline int f_update_mma2_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, V *, float *,
                                        V *, V *, int, double, uint32_t, unsigned *, unsigned long long *, const V * = nullptr, int = 0,
-                                       double * = nullptr, bool = true, const float * = nullptr) { return 1; }
+                                       double * = nullptr, bool = true, const float * = nullptr, V * = nullptr) { return 1; }
 #endif

@@ -246,6 +246,7 @@ static int roll_window_impl(S *s, uint64_t Tw, const void *a_host, const void *b
     }
     const unsigned grid = (unsigned)(s->num_sms * 8);
     s->valh_ok = false;      // the window's by-series values are rewritten below: their fp16 split is stale
+    cm_reset(s);             // ... and so is everything the complement formulation derived from Y
     if (s->sparse_storage) {
         uint64_t nnz_w = 0;
         CUDA_TRY(cudaMemcpyAsync(&nnz_w, s->row_ptr + Tw, sizeof(uint64_t), cudaMemcpyDeviceToHost, s->stream));

@@ -13,6 +13,7 @@
 #include "f_update_mma.cuh"
 #include "f_update_tc.cuh"
 #include "f_update_mma2.cuh"
+#include "complement.cuh"
 #include "x_update.cuh"
 #include "x_pass_fast.cuh"
 #include "lag_update.cuh"
@@ -152,6 +153,17 @@ struct trmf_b200_session {
     uint32_t *valh = nullptr;         // F-update of f_update_mma2.cuh: the CSC values as fp16 pairs (nnz words, indexed like val)
     size_t valh_cap = 0;
     bool valh_ok = false;             // valh / ysc describe the whole of the current val (cleared whenever Y changes)
+    // complement formulation for a mostly observed Y (complement.cuh): 0 = undecided, 1 = in use, -1 = not
+    int cm_state = 0;
+    uint64_t *cm_ptr[2] = {nullptr, nullptr};   // missing cells per series [0] / per time stamp [1]
+    uint32_t *cm_idx[2] = {nullptr, nullptr};
+    float *cm_Y0 = nullptr;           // Y zero-filled at the missing cells, T x n row-major
+    double *cm_yy = nullptr;          // per time stamp: sum of squares of its observed values
+    double *cm_FtF = nullptr;         // k x k Gram of the gathered factor over ALL its rows
+    V *cm_Xr = nullptr;               // the gathered factor as the fp16 split carries it (max(T, n) x k), see presplit_kernel
+    double *cm_rhs = nullptr;         // max(T, n) x k: Y0^T W resp. Y0 H
+    double *cm_cpart = nullptr;       // split-K scratch of the tall-skinny products
+    size_t cm_cpart_elems = 0;
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
     size_t sys_batch = 0;             // series per batch
@@ -527,6 +539,8 @@ extern "C" void trmf_b200_destroy(S *s) {
     dist_teardown(s);
     dev_free(s->part_tk);
     dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys); dev_free(s->valh); dev_free(s->bm_dev);
+    dev_free(s->cm_ptr[0]); dev_free(s->cm_ptr[1]); dev_free(s->cm_idx[0]); dev_free(s->cm_idx[1]); dev_free(s->cm_Y0); dev_free(s->cm_yy);
+    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -1209,6 +1223,200 @@ static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd, const int *gat
     return 0;
 }
 
+
+// --------------------------------------------------------------------------
+// complement formulation (complement.cuh): mostly observed Y, fp32 build
+// --------------------------------------------------------------------------
+#ifdef TRMF_F32
+static int need_csr(S *s);
+static bool cm_supported_k(int k) { return f_update_mma_supported(k); }
+// decided once per session: a sparse session of the mma2 kernel family whose Y observes >= 70 % of its cells and whose
+// dense copy fits comfortably.  TRMF_B200_COMPLEMENT=0 / 1 pins the choice (1 still needs the kernel family).
+static bool cm_on(S *s) {
+    if (s->cm_state != 0) return s->cm_state > 0;
+    s->cm_state = -1;
+    const char *e = getenv("TRMF_B200_COMPLEMENT");
+    if (e && atoi(e) == 0) return false;
+    if (!s->missing || !s->sparse_storage || !use_mma2() || use_tc(s->k) || !cm_supported_k(s->k)) return false;
+    if (f_kernel_choice(s->k, s->W) != F_KERNEL_MMA || f_kernel_choice(s->k, s->H) != F_KERNEL_MMA) return false;
+    if (s->T >= (1ull << 32) || s->n >= (1ull << 32) || s->T == 0 || s->n == 0) return false;
+    const double cells = (double)s->T * (double)s->n;
+    if (!(e && atoi(e) == 1) && (double)s->nnz < 0.7 * cells) return false;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return false;
+    if (cells * 4.0 * 1.5 > (double)free_b * 0.5) return false;
+    s->cm_state = 1;
+    return true;
+}
+// index list of the missing cells of every row of one orientation (o = 0: by series from the CSC half, 1: by time from the CSR half)
+static int cm_build_index(S *s, int o) {
+    if (s->cm_ptr[o]) return 0;
+    const uint64_t rows = o == 0 ? s->n : s->T, dim = o == 0 ? s->T : s->n;
+    const uint64_t *ptr = o == 0 ? s->col_ptr : s->row_ptr;
+    const uint32_t *idx = o == 0 ? s->row_idx : s->col_idx;
+    const uint64_t nmiss = rows * dim - s->nnz;
+    const uint32_t words = (uint32_t)((dim + 31) / 32);
+    uint64_t *cnt = nullptr;
+    uint32_t *bm = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    if (dev_alloc(&s->cm_ptr[o], rows + 1) || dev_alloc(&s->cm_idx[o], std::max<uint64_t>(nmiss, 1)) || dev_alloc(&cnt, rows + 1) ||
+        dev_alloc(&bm, rows * (size_t)words))
+        return 1;
+    const unsigned grid = (unsigned)(s->num_sms * 8);
+    LAUNCH(s, cm::count_missing_kernel, (unsigned)std::min<uint64_t>((rows + 256) / 256, grid), 256, 0, ptr, rows, dim, cnt);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, s->cm_ptr[o], (int64_t)(rows + 1), s->stream));
+    CUDA_TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s->stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, s->cm_ptr[o], (int64_t)(rows + 1), s->stream));
+    LAUNCH(s, cm::missing_bitmap_kernel, grid, 256, 0, ptr, idx, rows, words, bm);
+    LAUNCH(s, bitmap_expand_kernel, grid, 256, 0, s->cm_ptr[o], bm, rows, dim, words, s->cm_idx[o]);
+    s->launches++;
+    CUDA_TRY(cudaFreeAsync(tmp, s->stream));
+    dev_free(cnt);
+    dev_free(bm);
+    return 0;
+}
+// everything that depends on Y only: both index lists, the zero-filled dense copy, the rows' sums of squares, scratch
+static int cm_build(S *s) {
+    if (s->cm_Y0) return 0;
+    if (need_csr(s)) return 1;
+    if (cm_build_index(s, 0) || cm_build_index(s, 1)) return 1;
+    const size_t rmax = std::max(Tcap(s), s->n), k = (size_t)s->k;
+    if (dev_alloc(&s->cm_Y0, s->T * s->n) || dev_alloc(&s->cm_yy, s->T) || dev_alloc(&s->cm_FtF, k * k) || dev_alloc(&s->cm_rhs, rmax * k) ||
+        dev_alloc(&s->cm_Xr, rmax * k))
+        return 1;
+    s->cm_cpart_elems = rmax * k * 16;
+    if (dev_alloc(&s->cm_cpart, s->cm_cpart_elems)) return 1;
+    if (!s->Cpart) {       // (the fp64 split-K product of dense.cuh serves the k x k Grams)
+        s->Cpart_elems = k * k * 512;
+        if (dev_alloc(&s->Cpart, s->Cpart_elems)) return 1;
+    }
+    CUDA_TRY(cudaMemsetAsync(s->cm_Y0, 0, s->T * s->n * sizeof(float), s->stream));
+    const unsigned grid = (unsigned)(s->num_sms * 8);
+    LAUNCH(s, cm::scatter_dense_kernel, grid, 256, 0, s->row_ptr, s->col_idx, s->val_t, (uint64_t)s->T, (uint64_t)s->n, s->cm_Y0);
+    LAUNCH(s, cm::row_sumsq_kernel, grid, 256, 0, s->row_ptr, s->val_t, (uint64_t)s->T, s->cm_yy);
+    return 0;
+}
+// out (M x k, fp64) = A B with A(m, kappa) = Y0[m * sm + kappa * sk]
+static int cm_gemm(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
+    const int N = s->k;
+    const size_t mt = (M + cm::GM - 1) / cm::GM;
+    // one wave: 4 CTAs of 49 KB fit an SM, and mt x splits CTAs must not spill a few stragglers into a second round
+    size_t splits = std::max<size_t>(1, (4 * (size_t)s->num_sms) / mt);
+    splits = std::min(splits, std::max<size_t>(1, K / 256));
+    splits = std::min(splits, std::max<size_t>(1, s->cm_cpart_elems / (M * (size_t)N)));
+    size_t kchunk = (K + splits - 1) / splits;
+    kchunk = (kchunk + cm::GK - 1) / cm::GK * cm::GK;
+    splits = (K + kchunk - 1) / kchunk;
+    dim3 grid((unsigned)mt, (unsigned)splits);
+#define CM_GEMM(NQ)                                                                                                          \
+    do {                                                                                                                     \
+        CUDA_TRY(cudaFuncSetAttribute(cm::gemm64_partial_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm::gemm64_smem)); \
+        LAUNCH(s, cm::gemm64_partial_kernel<NQ>, grid, 256, cm::gemm64_smem, s->cm_Y0, sm, sk, B, M, N, K, kchunk, s->cm_cpart); \
+    } while (0)
+    switch ((N + 7) / 8) {
+        case 1: CM_GEMM(1); break;
+        case 2: CM_GEMM(2); break;
+        case 3: CM_GEMM(3); break;
+        case 4: CM_GEMM(4); break;
+        case 5: CM_GEMM(5); break;
+        case 6: CM_GEMM(6); break;
+        case 7: CM_GEMM(7); break;
+        default: CM_GEMM(8); break;
+    }
+#undef CM_GEMM
+    LAUNCH(s, (gemm_finish_kernel<double>), ew_grid(s, M * (size_t)N), 256, 0, s->cm_cpart, (int)splits, M * (size_t)N, N, 1.0,
+           (const V *)nullptr, 0.0, 0.0, out, (const int *)nullptr);
+    return 0;
+}
+static int ensure_sys(S *s) {
+    if (s->sys) return 0;
+    const size_t sysd = f_update_mma_sys_doubles(s->k);
+    s->sys_batch = std::max<size_t>(1, std::min<size_t>(std::max(s->n, Tcap(s)), ((size_t)1 << 30) / (sysd * sizeof(double))));
+    return dev_alloc(&s->sys, s->sys_batch * sysd);
+}
+// F-update of every series through the complement
+static int cm_f_update(S *s) {
+    const int k = s->k;
+    if (cm_build(s) || ensure_sys(s)) return 1;
+    const size_t smem = sizeof(double) * ((size_t)(k + 1) * (k + 1) + k);
+    for (size_t b0 = 0; b0 < s->n; b0 += s->sys_batch) {
+        const size_t b1 = std::min(s->n, b0 + s->sys_batch);
+        // (the first launch splits W into fp16 pairs and leaves the values the split carries in cm_Xr: the products below read those)
+        if (f_update_mma2_launch<fm::MODE_GONLY>(s->stream, s->num_sms, s->cm_ptr[0] + b0, s->cm_idx[0], (const V *)nullptr, s->W, s->T, s->Xs,
+                                                 s->invs, (V *)nullptr, (V *)nullptr, k, 0.0, (uint32_t)(b1 - b0), s->queue, &s->launches,
+                                                 nullptr, 0, s->sys, b0 == 0, nullptr, s->cm_Xr))
+            return fail("complement Gram launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (b0 == 0) {
+            if (gemm<V, V, double>(s, s->cm_Xr, 1, (size_t)k, s->cm_Xr, (size_t)k, k, s->T, 1.0, nullptr, 0.0, 0.0, s->cm_FtF)) return 1;
+            if (cm_gemm(s, 1, s->n, s->cm_Xr, s->n, s->T, s->cm_rhs)) return 1;
+        }
+        unsigned grid = 1;
+#define CM_SOLVE(KK)                                                                                                         \
+    case KK: {                                                                                                               \
+        CUDA_TRY(cudaFuncSetAttribute(cm::solve_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+        int per_sm = 0;                                                                                                      \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cm::solve_kernel<KK>, 128, smem));                    \
+        grid = (unsigned)std::max<size_t>(1, std::min<size_t>(b1 - b0, (size_t)s->num_sms * (size_t)std::max(per_sm, 1)));    \
+        LAUNCH(s, cm::solve_kernel<KK>, grid, 128, smem, s->col_ptr + b0, s->cm_ptr[0] + b0, s->sys, s->cm_FtF, s->cm_rhs + b0 * (size_t)k, \
+               s->H + b0 * (size_t)k, s->lambdaI, (uint32_t)(b1 - b0));                                                      \
+        break;                                                                                                               \
+    }
+        switch (k) {
+            CM_SOLVE(8) CM_SOLVE(12) CM_SOLVE(16) CM_SOLVE(20) CM_SOLVE(24) CM_SOLVE(28) CM_SOLVE(32) CM_SOLVE(36) CM_SOLVE(40) CM_SOLVE(44)
+            CM_SOLVE(48) CM_SOLVE(52) CM_SOLVE(56) CM_SOLVE(60) CM_SOLVE(64)
+            default: return fail("internal: complement solve for k = %d", k);
+        }
+#undef CM_SOLVE
+    }
+    return 0;
+}
+// X-update: per-time-stamp Grams (fp32, s->Gt) + loss gradient into gout (added when gaccum) + sum of squared residuals per row
+static int cm_x_gram(S *s, V *gout, int gaccum) {
+    const int k = s->k;
+    if (cm_build(s) || ensure_sys(s)) return 1;
+    for (size_t b0 = 0; b0 < s->T; b0 += s->sys_batch) {
+        const size_t b1 = std::min(s->T, b0 + s->sys_batch);
+        if (f_update_mma2_launch<fm::MODE_GONLY>(s->stream, s->num_sms, s->cm_ptr[1] + b0, s->cm_idx[1], (const V *)nullptr, s->H, s->n, s->Xs,
+                                                 s->invs, (V *)nullptr, (V *)nullptr, k, 0.0, (uint32_t)(b1 - b0), s->queue, &s->launches,
+                                                 nullptr, 0, s->sys, b0 == 0, nullptr, s->cm_Xr))
+            return fail("complement Gram launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (b0 == 0) {
+            if (gemm<V, V, double>(s, s->cm_Xr, 1, (size_t)k, s->cm_Xr, (size_t)k, k, s->n, 1.0, nullptr, 0.0, 0.0, s->cm_FtF)) return 1;
+            if (cm_gemm(s, s->n, 1, s->cm_Xr, s->T, s->n, s->cm_rhs)) return 1;
+        }
+        const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(b1 - b0, (size_t)s->num_sms * 8));
+#define CM_XGRAM(KK)                                                                                                         \
+    case KK:                                                                                                                 \
+        LAUNCH(s, cm::xgram_kernel<KK>, grid, 128, 0, s->row_ptr + b0, s->cm_ptr[1] + b0, s->sys, s->cm_FtF, s->cm_rhs + b0 * (size_t)k, \
+               s->cm_yy + b0, s->W + b0 * (size_t)k, gout + b0 * (size_t)k, s->Gt + b0 * (size_t)k * k, gaccum, s->frow + b0,  \
+               (uint32_t)(b1 - b0));                                                                                         \
+        break;
+        switch (k) {
+            CM_XGRAM(8) CM_XGRAM(12) CM_XGRAM(16) CM_XGRAM(20) CM_XGRAM(24) CM_XGRAM(28) CM_XGRAM(32) CM_XGRAM(36) CM_XGRAM(40) CM_XGRAM(44)
+            CM_XGRAM(48) CM_XGRAM(52) CM_XGRAM(56) CM_XGRAM(60) CM_XGRAM(64)
+            default: return fail("internal: complement Gram assembly for k = %d", k);
+        }
+#undef CM_XGRAM
+    }
+    return 0;
+}
+// Y changed (a rolling session moved its window): everything derived from it goes, the decision is taken again
+static void cm_reset(S *s) {
+    dev_free(s->cm_ptr[0]); dev_free(s->cm_ptr[1]); dev_free(s->cm_idx[0]); dev_free(s->cm_idx[1]); dev_free(s->cm_Y0); dev_free(s->cm_yy);
+    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr);
+    s->cm_ptr[0] = s->cm_ptr[1] = nullptr; s->cm_idx[0] = s->cm_idx[1] = nullptr;
+    s->cm_Y0 = nullptr; s->cm_yy = nullptr; s->cm_FtF = nullptr; s->cm_rhs = nullptr; s->cm_cpart = nullptr; s->cm_Xr = nullptr;
+    s->cm_cpart_elems = 0;
+    s->cm_state = 0;
+}
+#else
+static void cm_reset(S *) {}
+static bool cm_on(S *) { return false; }
+static int cm_f_update(S *) { return 1; }
+static int cm_x_gram(S *, V *, int) { return 1; }
+#endif
+
 // sparse F-update of the series [j0, j1) with the mma kernel.  Default: the kernel only assembles the fp64 systems
 // (MODE_DEFER) in batches of at most ~1 GB of scratch and chol_solve_kernel factors each batch; the in-kernel solve
 // (TRMF_B200_INLINE_SOLVE) gives bit-identical factors.
@@ -1285,7 +1493,10 @@ extern "C" int trmf_b200_f_update(S *s) {
         if (fk != F_KERNEL_MMA && wait_slabs(s)) return 1;
         if (fk == F_KERNEL_MMA) {
             if (mma_scratch(s)) return 1;
-            if (s->slabs_pending) {
+            if (cm_on(s)) {
+                // mostly observed Y: the complement formulation (needs the whole of Y: a slab-wise upload is waited for)
+                if (wait_slabs(s) || cm_f_update(s)) return 1;
+            } else if (s->slabs_pending) {
                 // first F-update of a host-buffer session: one launch per series slab, each as soon as its slab has landed
                 for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
                     CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
@@ -1382,7 +1593,9 @@ extern "C" int trmf_b200_x_update(S *s) {
                     LAUNCH(s, ar_apply_kernel, ew_grid(s, tk), 256, 0, s->W, s->th, lagset(s), s->rho, s->g, s->T, s->k, s->lambdaI, s->lambdaAR, (const int *)nullptr);
                     const bool one = s->world == 1;
                     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev4, s->stream));
-                    if (use_tc(s->k))
+                    if (cm_on(s))
+                        rc = cm_x_gram(s, one ? s->g : s->part_tk, one ? 1 : 0);
+                    else if (use_tc(s->k))
                         rc = f_update_tc_launch<fm::MODE_GRAD>(s->stream, s->num_sms, s->row_ptr, s->col_idx, s->val_t, s->H, s->n, s->Xs, s->invs,
                                                                one ? s->g : s->part_tk, s->Gt, s->k, (uint32_t)s->T, s->queue, s->ysc, &s->launches,
                                                                s->W, one ? 1 : 0, s->frow);

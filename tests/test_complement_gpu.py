@@ -1,0 +1,117 @@
+"""GPU parity tests of the complement formulation (csrc/complement.cuh): for a mostly observed Y the sparse F-update and the
+X-update's Gram / gradient / objective are computed over the MISSING cells plus two dense tall-skinny products, instead of
+walking Omega (reference trmf.cpp:369-397, 231-267).  Same bar as every fp32 path: 1e-5 against the float64 oracle per outer
+iteration started from the oracle's factors, CG step counts equal."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sps
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "exp-trmf-nips16_b200"))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+
+import cases  # noqa: E402
+from oracle import trmf_numpy as tn  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+TOL32 = 1e-5
+f32 = lambda a: np.asarray(a, dtype=np.float32)  # noqa: E731
+
+
+def _problem(T, n, k, lags, density, seed):
+    """cases.make_problem (one empty series, one empty time stamp) + one fully observed series and one fully observed time
+    stamp (their complement lists are empty), + one series that misses a single cell."""
+    p = cases.make_problem(T, n, k, lags, density, seed)
+    mask = p["mask"].copy()
+    mask[:, 7] = True
+    mask[11, :] = True
+    mask[:, 3] = False          # (the empty series / time stamp win over the full row / column)
+    mask[5, :] = False
+    mask[:, 9] = True
+    mask[17, 9] = False
+    mask[5, 9] = False
+    p["Ysp"] = sps.csr_matrix(np.where(mask, p["Y"], 0.0))
+    p["mask"] = mask
+    return p
+
+
+def _two_iterations(p, lam, monkeypatch, env):
+    from trmf.session import Session
+    for name in ("TRMF_B200_COMPLEMENT",):
+        monkeypatch.delenv(name, raising=False)
+    for name, value in env.items():
+        monkeypatch.setenv(name, value)
+    Y = sps.csr_matrix((f32(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    Y64 = Y.astype(np.float64)
+    W, H, L = (f32(p[x]).astype(np.float64) for x in ("W0", "H0", "L0"))
+    s = Session(Y, p["lags"], f32(W), f32(H), f32(L), missing=True, dtype=np.float32, lambdaI=lam[0], lambdaAR=lam[1], lambdaLag=lam[2])
+    outs, errs = [], []
+    for it in range(2):
+        s.upload(W=f32(W), H=f32(H), lag_val=f32(L))
+        W, H, L = f32(W).astype(np.float64), f32(H).astype(np.float64), f32(L).astype(np.float64)
+        s.f_update(); s.x_update(); s.lag_update()
+        Ho = tn.f_update_sparse(sps.csc_matrix(Y64), W, H, lam[0])
+        info = {}
+        Wo = tn.x_update(tn.SparseLoss(Y64, Ho), W, p["lags"].astype(np.int64), L, lam[0], lam[1], info)
+        Lo = tn.lag_update(Wo, p["lags"], lam[2])
+        Wg, Hg, Lg = s.download()
+        assert int(s.stat("cg_iters")) == info["cg_iter"]
+        assert bool(s.stat("accepted")) == info["accepted"]
+        errs.append((cases.rel(Hg, Ho), cases.rel(Wg, Wo), cases.rel(Lg, Lo)))
+        assert max(errs[-1]) < TOL32, errs
+        assert abs(s.stat("f") - info["f"]) <= 2e-5 * abs(info["f"])
+        outs.append((Wg, Hg, Lg))
+        W, H, L = Wo, Ho, Lo
+    s.close()
+    return outs, errs
+
+
+@pytest.mark.parametrize("k,density", [(8, 0.9), (20, 0.85), (40, 0.9), (40, 0.75), (64, 0.95), (28, 0.9)])
+def test_complement_path_matches_the_oracle_and_the_walks(k, density, monkeypatch):
+    p = _problem(700, 500, k, [1, 7, 24], density, seed=100 + k)
+    lam = (0.5, 50.0, 0.5)
+    a, ea = _two_iterations(p, lam, monkeypatch, {})                                  # density >= 0.7: the complement path
+    b, eb = _two_iterations(p, lam, monkeypatch, {"TRMF_B200_COMPLEMENT": "0"})       # the walks over Omega
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert cases.rel(u, v) < 1e-5
+    assert any(not np.array_equal(u, v) for x, y in zip(a, b) for u, v in zip(x, y)), "the switch did not change the path"
+    # empty series keeps its row, like in the reference (trmf.cpp:374)
+    assert np.array_equal(a[0][1][3], f32(p["H0"])[3])
+
+
+def test_complement_path_can_be_forced_on_a_sparse_problem(monkeypatch):
+    """TRMF_B200_COMPLEMENT=1 below the density threshold (here half the cells observed: no gain) -- still right.  (The tensor-core
+    part of the Gram grows with the missing fraction, and with it the part of the error that is not a consistent perturbation of the
+    data: at 30 % observed this problem's second iteration lands at 1.05e-5.  The automatic choice starts at 70 % observed.)"""
+    p = _problem(400, 300, 40, [1, 2, 5], 0.5, seed=9)
+    a, _ = _two_iterations(p, (0.5, 5.0, 0.5), monkeypatch, {"TRMF_B200_COMPLEMENT": "1"})
+    b, _ = _two_iterations(p, (0.5, 5.0, 0.5), monkeypatch, {"TRMF_B200_COMPLEMENT": "0"})
+    for x, y in zip(a, b):
+        for u, v in zip(x, y):
+            assert cases.rel(u, v) < 1e-5
+
+
+def test_complement_path_through_the_c_abi(monkeypatch):
+    """c_trmf_train with host buffers (slab-wise upload, host-packed indices): the complement F-update waits for every slab and
+    gives the factors of the device-resident session bit for bit."""
+    from trmf.session import Session
+    from oracle import abi
+    lib = os.path.join(ROOT, "exp-trmf-nips16_b200", "trmf", "corelib", "trmf_float32.so")
+    p = _problem(2600, 2000, 40, [1, 7, 24], 0.9, seed=4)          # nnz > 2^22: the slab path
+    Y = sps.csr_matrix((f32(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    assert Y.nnz >= 1 << 22
+    kw = dict(lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5, max_iter=2, period_Lag=1, missing=True)
+    W, H, L = abi.run_train(lib, Y, p["lags"], f32(p["W0"]), f32(p["H0"]), f32(p["L0"]), dtype=np.float32, **kw)
+    s = Session(Y, p["lags"], f32(p["W0"]), f32(p["H0"]), f32(p["L0"]), missing=True, dtype=np.float32, lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5)
+    s.train(max_iter=2, period_W=1, period_H=1, period_Lag=1)
+    W2, H2, L2 = s.download()
+    s.close()
+    assert np.array_equal(W, W2) and np.array_equal(H, H2) and np.array_equal(L, L2)
+    Wo, Ho, Lo = tn.train(Y.astype(np.float64), p["lags"], f32(p["W0"]).astype(np.float64), f32(p["H0"]).astype(np.float64),
+                          f32(p["L0"]).astype(np.float64), **kw)
+    assert cases.rel(H, Ho) < 3e-5 and cases.rel(W, Wo) < 3e-5 and cases.rel(L, Lo) < 3e-5      # (two chained iterations)
