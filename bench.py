@@ -492,10 +492,18 @@ def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
     fk = float(np.mean(fk_ms))
     achieved = bytes_f / (fk * 1e-3) / 1e9
     flops_f = nnz_loc * (k * k + 3 * k) + n_loc * (k ** 3 / 3 + 2 * k * k)
+    compl = s.stat("formulation") > 0
+    COMPL_NOTE = ("complement formulation (csrc/complement.cuh): Y observes >= 70 % of its cells, so the Gram is X^T X minus a gather over the "
+                  "MISSING cells and the right-hand sides are one fp64 tall-skinny product over the zero-filled dense Y; `achieved` keeps "
+                  "SURVEY 8d's per-observed-entry gather model, which this formulation no longer moves -- a fraction above 1 is the algorithm, "
+                  "not the memory system (DRAM traffic per launch is in `traffic`); the dominant kernel is the DFMA-bound product, see "
+                  "profiles/r02_launches_c2.txt")
     roofline = {"bound": "hbm", "kernel": "f_update (Gram + Cholesky per series)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(cfg_key, k, world), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_f, "kernel_ms": fk, "fp32_tflops": flops_f / (fk * 1e-3) / 1e12,
-                "entries_per_s": nnz_loc / (fk * 1e-3)}
+                "entries_per_s": nnz_loc / (fk * 1e-3), "formulation": "complement" if compl else "walk over the observed entries"}
+    if compl:
+        roofline["note"] = COMPL_NOTE
     # ---- second roofline: the X-update's Gram build with the fused loss value / gradient (rows = time stamps).
     # Algorithmic bytes: the same gather model, N(8+4k) + T(8+4k), plus the T k^2 fp32 Grams it stores.
     xg = float(np.mean(xg_ms)) if xg_ms and np.mean(xg_ms) > 0 else None
@@ -505,7 +513,7 @@ def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
         roofline_x = {"bound": "hbm", "kernel": "x_update Gram build + fused fun/grad (per time stamp)", "achieved": bytes_x / (xg * 1e-3) / 1e9,
                       "peak": peak, "unit": "GB/s", "frac": bytes_x / (xg * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(cfg_key, k, world, "x_gram"),
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_x, "kernel_ms": xg,
-                      "entries_per_s": nnz_loc / (xg * 1e-3)}
+                      "entries_per_s": nnz_loc / (xg * 1e-3), "formulation": "complement" if compl else "walk over the observed entries"}
 
     # ---- end to end through the public host-buffer API ----
     e2e = None if (args.no_e2e or light) else run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0,

@@ -84,80 +84,87 @@ __global__ void row_sumsq_kernel(const uint64_t *__restrict__ row_ptr, const flo
 // Cpart[split][m][c] = sum_{kappa in the split's range} A(m, kappa) * B[kappa][c],  A(m, kappa) = A[m * sm + kappa * sk] (one of sm, sk is 1),
 // B row-major (kappa x N), N <= 64; fp32 inputs, DFMA accumulation (B200 issues half as many DFMAs as FFMAs per clock -- and the
 // right-hand sides need it: on an ill-conditioned system a 1e-7 relative error of the right-hand side alone moves the solution by
-// 3e-5, tests/test_complement_gpu.py).  CTA tile: 128 rows x all N columns, 32 kappa per step staged in shared memory as doubles
-// while the next step's values are already in flight in registers; a thread owns 4 rows x ceil(N / 8) columns.  Same split-K /
-// finish scheme as dense.cuh (gemm_finish_kernel sums the splits in order).
+// 3e-5, tests/test_complement_gpu.py).  CTA = 4 warps on a tile of 128 rows x all N columns, 32 kappa per step staged in shared
+// memory as doubles while the next step's values are already in flight in registers.  A thread owns 4 rows x CPT columns, a warp
+// 32 rows x all columns.  Measured DFMA roof of one B200: 58 per clock and SM (tools/microbench_dfma.cu, profiles/).
+// Same split-K / finish scheme as dense.cuh (gemm_finish_kernel sums the splits in order).
 constexpr int GM = 128, GK = 32, GAS = GM + 2;     // (row stride of the A tile in doubles: 16-byte aligned)
-template <int NQ>
-__global__ void __launch_bounds__(256)
+template <int CPT>
+__global__ void __launch_bounds__(128, CPT <= 10 ? 3 : 2)
 gemm64_partial_kernel(const float *__restrict__ A, size_t sm, size_t sk, const float *__restrict__ B, size_t M, int N, size_t K,
                       size_t kchunk, double *__restrict__ Cpart) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    double (*As)[GAS] = reinterpret_cast<double (*)[GAS]>(smem_raw);                       // [GK][GAS]
-    double (*Bs)[64] = reinterpret_cast<double (*)[64]>(smem_raw + sizeof(double) * GK * GAS);   // [GK][64]
-    const int tid = threadIdx.x, lane = tid & 31, cg = tid >> 5;     // lane = row group (4 rows), warp = column group
+    double (*As)[GAS] = reinterpret_cast<double (*)[GAS]>(smem_raw);            // [GK][GAS]
+    double *Bs = reinterpret_cast<double *>(smem_raw + sizeof(double) * GK * GAS);   // [GK][N] (+ slack: the last column group may read past N)
+    // warp w owns rows 32 w .. 32 w + 31 of the tile; inside it lane = (column group, row group of 4): per kappa the warp touches
+    // 32 rows of A and all columns of B once (9 shared-memory wavefronts for 4 * CPT DFMAs per lane)
+    const int tid = threadIdx.x, lane = tid & 31, rg = 8 * (tid >> 5) + (lane & 7), cg = lane >> 3;
     const size_t m0 = (size_t)blockIdx.x * GM;
     const size_t k0 = (size_t)blockIdx.y * kchunk, k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
-    double acc[4][NQ];
+    double acc[4][CPT];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) acc[i][q] = 0.0;
-    float ra[16], rb[8];       // the next step's share of the A tile (128 x 32 / 256) and of the B tile (32 x 64 / 256)
+        for (int q = 0; q < CPT; ++q) acc[i][q] = 0.0;
+    // this thread's share of a step's tiles: A tile element u = (row am + au * u, kappa ak + (1 - au > 0 ? u : 0)) -- either it
+    // walks kappa (rows contiguous in memory: row = tid, kappa = u) or rows (kappa contiguous: kappa = tid % 32, row = tid / 32 + 4 u);
+    // B tile = GK * N consecutive floats, element tid + 128 u
+    constexpr int NA = GM * GK / 128, NBL = (GK * 64 + 127) / 128;
+    const bool kfast = sk == 1;
+    const int a_row0 = kfast ? tid >> 5 : tid, a_k0 = kfast ? tid & 31 : 0;
+    const int a_drow = kfast ? 4 : 0, a_dk = kfast ? 0 : 1;
+    const size_t a_step = kfast ? 4 * sm : sk;
+    const int nb = GK * N;
+    float ra[NA], rb[NBL];
     auto fetch = [&](size_t kk) {
+        const float *pa = A + (m0 + a_row0) * sm + (kk + a_k0) * sk;
+        if (m0 + GM <= M && kk + GK <= k1) {         // interior tile: no bounds to check
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int p = tid + 256 * u;
-            int kq, mq;
-            if (sk == 1) { kq = p % GK; mq = p / GK; } else { mq = p % GM; kq = p / GM; }
-            const size_t m = m0 + mq, kap = kk + kq;
-            ra[u] = (m < M && kap < k1) ? __ldg(A + m * sm + kap * sk) : 0.f;
-        }
+            for (int u = 0; u < NA; ++u) ra[u] = __ldg(pa + u * a_step);
+        } else {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const int p = tid + 256 * u, c = p & 63, kq = p >> 6;
-            const size_t kap = kk + kq;
-            rb[u] = (c < N && kap < k1) ? __ldg(B + kap * N + c) : 0.f;
+            for (int u = 0; u < NA; ++u)
+                ra[u] = (m0 + a_row0 + a_drow * u < M && kk + a_k0 + a_dk * u < k1) ? __ldg(pa + u * a_step) : 0.f;
         }
+        const float *pb = B + kk * N + tid;
+        const int lim = (kk + GK <= k1) ? nb : (int)(k1 - kk) * N;
+#pragma unroll
+        for (int u = 0; u < NBL; ++u) rb[u] = (tid + 128 * u < lim) ? __ldg(pb + 128 * u) : 0.f;
     };
     fetch(k0);
     for (size_t kk = k0; kk < k1; kk += GK) {
         __syncthreads();          // the previous step's tiles are consumed
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-            const int p = tid + 256 * u;
-            int kq, mq;
-            if (sk == 1) { kq = p % GK; mq = p / GK; } else { mq = p % GM; kq = p / GM; }
-            As[kq][mq] = (double)ra[u];
-        }
+        for (int u = 0; u < NA; ++u) As[a_k0 + a_dk * u][a_row0 + a_drow * u] = (double)ra[u];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { const int p = tid + 256 * u; Bs[p >> 6][p & 63] = (double)rb[u]; }
+        for (int u = 0; u < NBL; ++u) if (tid + 128 * u < nb) Bs[tid + 128 * u] = (double)rb[u];
         __syncthreads();
         if (kk + GK < k1) fetch(kk + GK);
-#pragma unroll 4
+        const double *bp = Bs + cg * CPT;
+#pragma unroll 2
         for (int kq = 0; kq < GK; ++kq) {
-            const double2 a01 = *reinterpret_cast<const double2 *>(&As[kq][4 * lane]), a23 = *reinterpret_cast<const double2 *>(&As[kq][4 * lane + 2]);
+            const double2 a01 = *reinterpret_cast<const double2 *>(&As[kq][4 * rg]), a23 = *reinterpret_cast<const double2 *>(&As[kq][4 * rg + 2]);
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
-                const double b = Bs[kq][cg + 8 * q];
-                acc[0][q] = fma(a01.x, b, acc[0][q]);
-                acc[1][q] = fma(a01.y, b, acc[1][q]);
-                acc[2][q] = fma(a23.x, b, acc[2][q]);
-                acc[3][q] = fma(a23.y, b, acc[3][q]);
+            for (int q = 0; q < CPT; q += 2) {
+                const double2 b = *reinterpret_cast<const double2 *>(bp + kq * N + q);
+                acc[0][q] = fma(a01.x, b.x, acc[0][q]);         acc[0][q + 1] = fma(a01.x, b.y, acc[0][q + 1]);
+                acc[1][q] = fma(a01.y, b.x, acc[1][q]);         acc[1][q + 1] = fma(a01.y, b.y, acc[1][q + 1]);
+                acc[2][q] = fma(a23.x, b.x, acc[2][q]);         acc[2][q + 1] = fma(a23.x, b.y, acc[2][q + 1]);
+                acc[3][q] = fma(a23.y, b.x, acc[3][q]);         acc[3][q + 1] = fma(a23.y, b.y, acc[3][q + 1]);
             }
         }
     }
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const size_t m = m0 + 4 * lane + i;
+        const size_t m = m0 + 4 * rg + i;
         if (m < M) {
             double *dst = Cpart + ((size_t)blockIdx.y * M + m) * N;
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) { const int c = cg + 8 * q; if (c < N) dst[c] = acc[i][q]; }
+            for (int q = 0; q < CPT; ++q) { const int c = cg * CPT + q; if (c < N) dst[c] = acc[i][q]; }
         }
     }
 }
-constexpr size_t gemm64_smem = sizeof(double) * ((size_t)GK * GAS + (size_t)GK * 64);
+template <int CPT> constexpr size_t gemm64_smem() { return sizeof(double) * ((size_t)GK * GAS + (size_t)GK * 64 + 16); }
 
 // ---- F-update: (X^T X - Gmiss_j + lambda I) f = rhs_j, one CTA per system at a time (fp64 Cholesky of common.cuh) ----
 // sys[j] = the (K+1) x (K+1) lower-triangle layout MODE_GONLY leaves (only read when the series has missing cells), XtX = K x K fp64

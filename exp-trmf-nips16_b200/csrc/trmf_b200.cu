@@ -1297,37 +1297,40 @@ static int cm_build(S *s) {
     LAUNCH(s, cm::row_sumsq_kernel, grid, 256, 0, s->row_ptr, s->val_t, (uint64_t)s->T, s->cm_yy);
     return 0;
 }
-// out (M x k, fp64) = A B with A(m, kappa) = Y0[m * sm + kappa * sk]
-static int cm_gemm(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
+template <int CPT>
+static int cm_gemm_t(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
     const int N = s->k;
-    const size_t mt = (M + cm::GM - 1) / cm::GM;
-    // one wave: 4 CTAs of 49 KB fit an SM, and mt x splits CTAs must not spill a few stragglers into a second round
-    size_t splits = std::max<size_t>(1, (4 * (size_t)s->num_sms) / mt);
+    auto kfn = cm::gemm64_partial_kernel<CPT>;
+    const size_t smem = cm::gemm64_smem<CPT>();
+    CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem));
+    const size_t slots = (size_t)s->num_sms * (size_t)std::max(per_sm, 1), mt = (M + cm::GM - 1) / cm::GM;
+    // whole waves: mt x splits CTAs should not spill a few stragglers into another round of the resident CTAs
+    size_t splits = std::max<size_t>(1, slots / mt);
     splits = std::min(splits, std::max<size_t>(1, K / 256));
     splits = std::min(splits, std::max<size_t>(1, s->cm_cpart_elems / (M * (size_t)N)));
     size_t kchunk = (K + splits - 1) / splits;
     kchunk = (kchunk + cm::GK - 1) / cm::GK * cm::GK;
     splits = (K + kchunk - 1) / kchunk;
     dim3 grid((unsigned)mt, (unsigned)splits);
-#define CM_GEMM(NQ)                                                                                                          \
-    do {                                                                                                                     \
-        CUDA_TRY(cudaFuncSetAttribute(cm::gemm64_partial_kernel<NQ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cm::gemm64_smem)); \
-        LAUNCH(s, cm::gemm64_partial_kernel<NQ>, grid, 256, cm::gemm64_smem, s->cm_Y0, sm, sk, B, M, N, K, kchunk, s->cm_cpart); \
-    } while (0)
-    switch ((N + 7) / 8) {
-        case 1: CM_GEMM(1); break;
-        case 2: CM_GEMM(2); break;
-        case 3: CM_GEMM(3); break;
-        case 4: CM_GEMM(4); break;
-        case 5: CM_GEMM(5); break;
-        case 6: CM_GEMM(6); break;
-        case 7: CM_GEMM(7); break;
-        default: CM_GEMM(8); break;
-    }
-#undef CM_GEMM
+    LAUNCH(s, kfn, grid, 128, smem, s->cm_Y0, sm, sk, B, M, N, K, kchunk, s->cm_cpart);
     LAUNCH(s, (gemm_finish_kernel<double>), ew_grid(s, M * (size_t)N), 256, 0, s->cm_cpart, (int)splits, M * (size_t)N, N, 1.0,
            (const V *)nullptr, 0.0, 0.0, out, (const int *)nullptr);
     return 0;
+}
+// out (M x k, fp64) = A B with A(m, kappa) = Y0[m * sm + kappa * sk]
+static int cm_gemm(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
+    switch (2 * ((s->k + 7) / 8)) {      // columns per thread: 4 column groups, an even number each
+        case 2: return cm_gemm_t<2>(s, sm, sk, B, M, K, out);
+        case 4: return cm_gemm_t<4>(s, sm, sk, B, M, K, out);
+        case 6: return cm_gemm_t<6>(s, sm, sk, B, M, K, out);
+        case 8: return cm_gemm_t<8>(s, sm, sk, B, M, K, out);
+        case 10: return cm_gemm_t<10>(s, sm, sk, B, M, K, out);
+        case 12: return cm_gemm_t<12>(s, sm, sk, B, M, K, out);
+        case 14: return cm_gemm_t<14>(s, sm, sk, B, M, K, out);
+        default: return cm_gemm_t<16>(s, sm, sk, B, M, K, out);
+    }
 }
 static int ensure_sys(S *s) {
     if (s->sys) return 0;
@@ -1872,6 +1875,7 @@ extern "C" double trmf_b200_stat(S *s, int32_t which) {
         case TRMF_STAT_ACTRED: return s->st_actred;
         case TRMF_STAT_COLLECTIVES: return (double)s->collectives;
         case TRMF_STAT_X_GRAM_MS: return s->ms_xg;
+        case TRMF_STAT_FORMULATION: return s->cm_state > 0 ? 1.0 : 0.0;
     }
     return NAN;
 }

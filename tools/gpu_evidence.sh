@@ -5,7 +5,9 @@
 #
 # quick (default, ~4 min): GPU test suite, smoke, bench lines for C2 / C3 (with parity, roofline_x, strong C5 record), reference arm,
 #                          rolling_validate runs, ncu launch list of the bench command.
-# full  (+ ~3 min):        also the ncu --set full capture of the two Gram launches (F-update, X-update Gram build) and the C4 line.
+# full  (+ ~4 min):        also the ncu --set full captures (the kernels of one outer iteration of the default path: complement
+#                          Gram, fp64 product, solve, Gram assembly; and the two Gram launches of the walk over Omega with
+#                          TRMF_B200_COMPLEMENT=0), the standalone kernel test, the walk-path bench line and the C4 line.
 # Outputs go to gpurun_out/ (merged back by gpurun); copy what should be judged into profiles/ (names r<round>_*).
 # Numbers printed by a command running under ncu are never bench values.
 set -u
@@ -28,8 +30,13 @@ timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --
 python tools/ncu_summary.py "$out/${tag}_launches_c2.csv" > "$out/${tag}_launches_c2.txt"; head -14 "$out/${tag}_launches_c2.txt"
 
 if [ "$mode" = "full" ]; then
-    timeout 500 ncu --set full --clock-control none --import-source on -k regex:f_update_mma -s 2 -c 2 -o "$out/${tag}_f_update_mma_full" -f \
-        python bench.py --steps 1 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_full.log" 2>&1
+    timeout 500 ncu --set full --clock-control none --import-source on -k 'regex:gemm64|f_update_mma2|solve_kernel|xgram_kernel' -s 6 -c 6 \
+        -o "$out/${tag}_complement_full" -f python bench.py --steps 1 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_full.log" 2>&1
+    TRMF_B200_COMPLEMENT=0 timeout 500 ncu --set full --clock-control none --import-source on -k regex:f_update_mma2 -s 2 -c 2 \
+        -o "$out/${tag}_mma2_k40_full" -f python bench.py --steps 1 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_full2.log" 2>&1
+    TRMF_B200_COMPLEMENT=0 timeout 400 python bench.py --strong none --no-cpu-baseline > "$out/${tag}_bench_c2_n1_walk.json" 2> "$out/${tag}_bench_c2_n1_walk.err"
+    for a in "40 small" "64 small" "20 small" "40 c2" "64 c5"; do echo "=== $a"; timeout 120 tools/test_f_update_mma2 $a 2>&1 | tail -8; done > "$out/${tag}_test_f_update_mma2.txt" 2>&1
+    tools/microbench_dfma > "$out/${tag}_microbench_dfma.txt" 2>&1
     timeout 400 python bench.py --config c4 --no-e2e --strong none > "$out/${tag}_bench_c4_n1.json" 2> "$out/${tag}_bench_c4_n1.err"
 fi
 echo "== done ($mode)"
