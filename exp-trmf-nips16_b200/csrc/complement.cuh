@@ -80,35 +80,46 @@ __global__ void row_sumsq_kernel(const uint64_t *__restrict__ row_ptr, const flo
     }
 }
 
-// ---- tall-skinny product in fp64 ----
+// ---- tall-skinny product in fp64 on the DMMA path ----
 // Cpart[split][m][c] = sum_{kappa in the split's range} A(m, kappa) * B[kappa][c],  A(m, kappa) = A[m * sm + kappa * sk] (one of sm, sk is 1),
-// B row-major (kappa x N), N <= 64; fp32 inputs, DFMA accumulation (B200 issues half as many DFMAs as FFMAs per clock -- and the
-// right-hand sides need it: on an ill-conditioned system a 1e-7 relative error of the right-hand side alone moves the solution by
-// 3e-5, tests/test_complement_gpu.py).  CTA = 4 warps on a tile of 128 rows x all N columns, 32 kappa per step staged in shared
-// memory as doubles while the next step's values are already in flight in registers.  A thread owns 4 rows x CPT columns, a warp
-// 32 rows x all columns.  Measured DFMA roof of one B200: 58 per clock and SM (tools/microbench_dfma.cu, profiles/).
+// B row-major (kappa x N), N <= 64; fp32 inputs, fp64 products and sums (the right-hand sides need it: on an ill-conditioned system a
+// 1e-7 relative error of the right-hand side alone moves the solution by 3e-5, tests/test_complement_gpu.py).
+//
+// mma.sync.m8n8k4.f64 (SASS DMMA.8x8x4) runs at the rate of the DFMA pipe on B200 -- 63.5 against 60.6 MAC per clock and SM,
+// tools/microbench_dfma.cu -- but takes its operands spread over the warp: 9 doubles per lane from shared memory for 20 DMMAs
+// (160 MACs per lane) at k = 40, where a register-tiled DFMA loop needs 14 for 40.  Two DFMA versions (8 column groups of 5; warp-owned
+// 32-row tiles of 4 x 10 per lane) were bound by exactly that: an LDS.128 costs 4 shared-memory wavefronts whether its lanes share an
+// address or not, 28 wavefronts per kappa and warp against 20 DFMA issue cycles per SM sub-partition -- 7 of the 17.6 TDFMA/s the
+// pipe delivers (profiles/r02_gemm64_history.md).
+//
+// CTA = 4 warps on a tile of 128 rows x all N columns, 32 kappa per step staged in shared memory as doubles while the next step's values
+// are already in flight in registers; warp w owns rows 32 w .. 32 w + 31 as 4 x NB accumulator tiles of 8 x 8.  Row strides of both
+// tiles are 4 mod 16 doubles, so the 16 lanes of a half warp (4 kappa x 4 rows / columns) hit 16 different 8-byte banks.
 // Same split-K / finish scheme as dense.cuh (gemm_finish_kernel sums the splits in order).
-constexpr int GM = 128, GK = 32, GAS = GM + 2;     // (row stride of the A tile in doubles: 16-byte aligned)
-template <int CPT>
-__global__ void __launch_bounds__(128, CPT <= 10 ? 3 : 2)
+constexpr int GM = 128, GK = 32, GAS = GM + 4;
+__device__ __forceinline__ void dmma884(double (&c)[2], const double a, const double b) {
+    asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+__host__ __device__ inline int gemm64_bstride(int N) { return (N % 8 == 4) ? N : N + 4; }      // N % 4 == 0
+template <int NB>
+__global__ void __launch_bounds__(128, NB <= 5 ? 3 : 2)
 gemm64_partial_kernel(const float *__restrict__ A, size_t sm, size_t sk, const float *__restrict__ B, size_t M, int N, size_t K,
                       size_t kchunk, double *__restrict__ Cpart) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double (*As)[GAS] = reinterpret_cast<double (*)[GAS]>(smem_raw);            // [GK][GAS]
-    double *Bs = reinterpret_cast<double *>(smem_raw + sizeof(double) * GK * GAS);   // [GK][N] (+ slack: the last column group may read past N)
-    // warp w owns rows 32 w .. 32 w + 31 of the tile; inside it lane = (column group, row group of 4): per kappa the warp touches
-    // 32 rows of A and all columns of B once (9 shared-memory wavefronts for 4 * CPT DFMAs per lane)
-    const int tid = threadIdx.x, lane = tid & 31, rg = 8 * (tid >> 5) + (lane & 7), cg = lane >> 3;
+    double *Bs = reinterpret_cast<double *>(smem_raw + sizeof(double) * GK * GAS);   // [GK][nbs] (+ slack: the last 8-column block may reach past N)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;      // fragment coordinates: row (A) / column (B) within the 8-block, kappa within the step of 4
+    const int nbs = gemm64_bstride(N);
     const size_t m0 = (size_t)blockIdx.x * GM;
     const size_t k0 = (size_t)blockIdx.y * kchunk, k1 = (k0 + kchunk < K) ? k0 + kchunk : K;
-    double acc[4][CPT];
+    double acc[4][NB][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int q = 0; q < CPT; ++q) acc[i][q] = 0.0;
-    // this thread's share of a step's tiles: A tile element u = (row am + au * u, kappa ak + (1 - au > 0 ? u : 0)) -- either it
-    // walks kappa (rows contiguous in memory: row = tid, kappa = u) or rows (kappa contiguous: kappa = tid % 32, row = tid / 32 + 4 u);
-    // B tile = GK * N consecutive floats, element tid + 128 u
+        for (int q = 0; q < NB; ++q) acc[i][q][0] = acc[i][q][1] = 0.0;
+    // this thread's share of a step's tiles: A tile element u = either (row tid, kappa u) -- rows contiguous in memory -- or
+    // (row tid / 32 + 4 u, kappa tid % 32) -- kappa contiguous; B tile = GK * N consecutive floats, element tid + 128 u
     constexpr int NA = GM * GK / 128, NBL = (GK * 64 + 127) / 128;
     const bool kfast = sk == 1;
     const int a_row0 = kfast ? tid >> 5 : tid, a_k0 = kfast ? tid & 31 : 0;
@@ -131,40 +142,55 @@ gemm64_partial_kernel(const float *__restrict__ A, size_t sm, size_t sk, const f
 #pragma unroll
         for (int u = 0; u < NBL; ++u) rb[u] = (tid + 128 * u < lim) ? __ldg(pb + 128 * u) : 0.f;
     };
+    // B tile element p = tid + 128 u sits at row p / N, column p % N: walk (row, column) instead of dividing
+    const int b_r0 = tid / N, b_c0 = tid - b_r0 * N, b_dr = 128 / N, b_dc = 128 - b_dr * N;
+    for (int p = tid; p < GK * nbs + 16; p += 128) Bs[p] = 0.0;     // (padding columns and the slack stay finite)
     fetch(k0);
     for (size_t kk = k0; kk < k1; kk += GK) {
         __syncthreads();          // the previous step's tiles are consumed
 #pragma unroll
         for (int u = 0; u < NA; ++u) As[a_k0 + a_dk * u][a_row0 + a_drow * u] = (double)ra[u];
+        {
+            int r = b_r0, c = b_c0;
 #pragma unroll
-        for (int u = 0; u < NBL; ++u) if (tid + 128 * u < nb) Bs[tid + 128 * u] = (double)rb[u];
-        __syncthreads();
-        if (kk + GK < k1) fetch(kk + GK);
-        const double *bp = Bs + cg * CPT;
-#pragma unroll 2
-        for (int kq = 0; kq < GK; ++kq) {
-            const double2 a01 = *reinterpret_cast<const double2 *>(&As[kq][4 * rg]), a23 = *reinterpret_cast<const double2 *>(&As[kq][4 * rg + 2]);
-#pragma unroll
-            for (int q = 0; q < CPT; q += 2) {
-                const double2 b = *reinterpret_cast<const double2 *>(bp + kq * N + q);
-                acc[0][q] = fma(a01.x, b.x, acc[0][q]);         acc[0][q + 1] = fma(a01.x, b.y, acc[0][q + 1]);
-                acc[1][q] = fma(a01.y, b.x, acc[1][q]);         acc[1][q + 1] = fma(a01.y, b.y, acc[1][q + 1]);
-                acc[2][q] = fma(a23.x, b.x, acc[2][q]);         acc[2][q + 1] = fma(a23.x, b.y, acc[2][q + 1]);
-                acc[3][q] = fma(a23.y, b.x, acc[3][q]);         acc[3][q + 1] = fma(a23.y, b.y, acc[3][q + 1]);
+            for (int u = 0; u < NBL; ++u) {
+                if (tid + 128 * u < nb) Bs[r * nbs + c] = (double)rb[u];
+                r += b_dr; c += b_dc;
+                if (c >= N) { c -= N; ++r; }
             }
         }
+        __syncthreads();
+        if (kk + GK < k1) fetch(kk + GK);
+        const double *ap = &As[fk][32 * warp + fr], *bp = Bs + fk * nbs + fr;
+#pragma unroll 2
+        for (int kq = 0; kq < GK; kq += 4) {
+            double a[4], b[NB];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = ap[kq * GAS + 8 * i];
+#pragma unroll
+            for (int q = 0; q < NB; ++q) b[q] = bp[kq * nbs + 8 * q];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int q = 0; q < NB; ++q) dmma884(acc[i][q], a[i], b[q]);
+        }
     }
+    // accumulator tile (i, q): lane holds row fr, columns 2 fk and 2 fk + 1
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const size_t m = m0 + 4 * rg + i;
+        const size_t m = m0 + 32 * warp + 8 * i + fr;
         if (m < M) {
             double *dst = Cpart + ((size_t)blockIdx.y * M + m) * N;
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) { const int c = cg * CPT + q; if (c < N) dst[c] = acc[i][q]; }
+            for (int q = 0; q < NB; ++q) {
+                const int c = 8 * q + 2 * fk;
+                if (c < N) dst[c] = acc[i][q][0];
+                if (c + 1 < N) dst[c + 1] = acc[i][q][1];
+            }
         }
     }
 }
-template <int CPT> constexpr size_t gemm64_smem() { return sizeof(double) * ((size_t)GK * GAS + (size_t)GK * 64 + 16); }
+template <int NB> constexpr size_t gemm64_smem() { return sizeof(double) * ((size_t)GK * GAS + (size_t)GK * 68 + 16); }
 
 // ---- F-update: (X^T X - Gmiss_j + lambda I) f = rhs_j, one CTA per system at a time (fp64 Cholesky of common.cuh) ----
 // sys[j] = the (K+1) x (K+1) lower-triangle layout MODE_GONLY leaves (only read when the series has missing cells), XtX = K x K fp64

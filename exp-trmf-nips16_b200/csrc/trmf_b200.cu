@@ -1297,11 +1297,11 @@ static int cm_build(S *s) {
     LAUNCH(s, cm::row_sumsq_kernel, grid, 256, 0, s->row_ptr, s->val_t, (uint64_t)s->T, s->cm_yy);
     return 0;
 }
-template <int CPT>
+template <int NB>
 static int cm_gemm_t(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
     const int N = s->k;
-    auto kfn = cm::gemm64_partial_kernel<CPT>;
-    const size_t smem = cm::gemm64_smem<CPT>();
+    auto kfn = cm::gemm64_partial_kernel<NB>;
+    const size_t smem = cm::gemm64_smem<NB>();
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem));
@@ -1321,15 +1321,15 @@ static int cm_gemm_t(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K,
 }
 // out (M x k, fp64) = A B with A(m, kappa) = Y0[m * sm + kappa * sk]
 static int cm_gemm(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
-    switch (2 * ((s->k + 7) / 8)) {      // columns per thread: 4 column groups, an even number each
+    switch ((s->k + 7) / 8) {      // 8-column accumulator blocks
+        case 1: return cm_gemm_t<1>(s, sm, sk, B, M, K, out);
         case 2: return cm_gemm_t<2>(s, sm, sk, B, M, K, out);
+        case 3: return cm_gemm_t<3>(s, sm, sk, B, M, K, out);
         case 4: return cm_gemm_t<4>(s, sm, sk, B, M, K, out);
+        case 5: return cm_gemm_t<5>(s, sm, sk, B, M, K, out);
         case 6: return cm_gemm_t<6>(s, sm, sk, B, M, K, out);
-        case 8: return cm_gemm_t<8>(s, sm, sk, B, M, K, out);
-        case 10: return cm_gemm_t<10>(s, sm, sk, B, M, K, out);
-        case 12: return cm_gemm_t<12>(s, sm, sk, B, M, K, out);
-        case 14: return cm_gemm_t<14>(s, sm, sk, B, M, K, out);
-        default: return cm_gemm_t<16>(s, sm, sk, B, M, K, out);
+        case 7: return cm_gemm_t<7>(s, sm, sk, B, M, K, out);
+        default: return cm_gemm_t<8>(s, sm, sk, B, M, K, out);
     }
 }
 static int ensure_sys(S *s) {
