@@ -21,11 +21,14 @@ from ctypes import POINTER, byref, c_double, c_int32, c_uint32
 import numpy as np
 import scipy.sparse as smat
 
+
 try:
     from .rf_util import PyMatrix, fillprototype, load_dynamic_library
 except ImportError:  # running as a script, like the reference allows
     from rf_util import PyMatrix, fillprototype, load_dynamic_library
 
+
+_RNG_LOCK = __import__("threading").Lock()   # np.random's global stream is shared by every thread (Model.initialize)
 
 class corelib(object):
     """The float32 / float64 pair of CUDA libraries (reference trmf.py:19-75)."""
@@ -233,8 +236,6 @@ class Model(object):
     # ---- initialisation / warm start (trmf.py:222-251) ----
     @classmethod
     def initialize(cls, Y, lag_set, k, warm_start_model=None, seed=None, dtype=None, transform=None, _transform_stats=None):
-        if seed is not None:
-            np.random.seed(seed)
         if dtype is None:
             dtype = Y.dtype
         m, n = Y.shape[0], Y.shape[1]
@@ -243,10 +244,14 @@ class Model(object):
         W = np.zeros((m, k), dtype=dtype, order="C")
         H = np.zeros((n, k), dtype=dtype, order="C")
         lag_val = np.zeros((L, k), dtype=dtype, order="F")
-        # draw order W, H, lag_val after the seed -- the reference's stream (trmf.py:234-236)
-        W[:] = np.random.rand(m, k)
-        H[:] = np.random.rand(n, k)
-        lag_val[:] = np.random.randn(L, k)
+        # draw order W, H, lag_val after the seed -- the reference's stream (trmf.py:234-236), NumPy's global generator.
+        # Seed + draws are one critical section: grid_search(workers > 1) initialises models from several threads.
+        with _RNG_LOCK:
+            if seed is not None:
+                np.random.seed(seed)
+            W[:] = np.random.rand(m, k)
+            H[:] = np.random.rand(n, k)
+            lag_val[:] = np.random.randn(L, k)
         if warm_start_model is not None:
             prev = warm_start_model
             assert prev.k == k
@@ -438,14 +443,21 @@ def _rolling_resident(Y, lag_set, k, window_size, nr_windows, lambdaI, lambdaAR,
     return Metrics.generate(trueY, forecastY, missing=missing)
 
 
-def grid_search(Y, lag_set, grid_params, pkl_file=None, **kw_args):
+def grid_search(Y, lag_set, grid_params, pkl_file=None, workers=1, **kw_args):
     """Exhaustive search over ``grid_params`` (dict name -> list of values),
     ranking by ``m_nd`` (reference trmf.py:331-346).  Every grid point is one
     ``rolling_validate``; on the resident path (its default for a dense float
     array) consecutive grid points with the same (k, missing, resident length =
     T - window_size, lag set, dtype) share one copy of Y in HBM instead of
     re-ingesting it nr_windows times per point; at most one session stays parked,
-    and a session that does not fit falls back to the per-window path."""
+    and a session that does not fit falls back to the per-window path.
+
+    ``workers`` > 1 (an addition; the reference runs the grid serially) trains that
+    many grid points at the same time: each worker thread owns its resident session
+    (its own copy of Y in HBM and its own CUDA stream), so the small launch-bound
+    kernels of the reference's data sets (370 x 26 304, 963 x 10 560) overlap on the
+    device.  Every grid point computes exactly what it computes alone -- results, the
+    best point and the print-out are the serial run's."""
     names = list(grid_params.keys())
     combos = list(itertools.product(*[grid_params[name] for name in names]))
     # Grid points that can share a resident session (same k, window_size, missing, lag set) run back to back, so that
@@ -457,18 +469,43 @@ def grid_search(Y, lag_set, grid_params, pkl_file=None, **kw_args):
         return (repr(kws.get("k", 40)), repr(kws.get("window_size", 24)), repr(kws.get("missing", True)))
     order = sorted(range(len(combos)), key=lambda i: share_key(combos[i]))   # (stable: ties keep the grid's order)
     done = {}
-    sessions = {}
+    parked = []          # one dict of parked sessions per worker thread
+
+    def run(i, sessions):
+        kws = dict(kw_args)
+        kws.update(zip(names, combos[i]))
+        return {"kws": kws, "metrics": rolling_validate(Y, lag_set, _sessions=sessions, **kws)}
+
+    def record(i, res):
+        done[i] = res
+        if pkl_file is not None:
+            with open(pkl_file, "wb") as fh:
+                pickle.dump([done[j] for j in sorted(done)], fh)
+
     try:
-        for i in order:
-            kws = dict(kw_args)
-            kws.update(zip(names, combos[i]))
-            done[i] = {"kws": kws, "metrics": rolling_validate(Y, lag_set, _sessions=sessions, **kws)}
-            if pkl_file is not None:
-                with open(pkl_file, "wb") as fh:
-                    pickle.dump([done[j] for j in sorted(done)], fh)
+        if workers is None or workers <= 1 or len(order) <= 1:
+            parked.append({})
+            for i in order:
+                record(i, run(i, parked[0]))
+        else:
+            import threading
+            from concurrent.futures import ThreadPoolExecutor
+            tls, lock = threading.local(), threading.Lock()
+
+            def worker(i):
+                if not hasattr(tls, "sessions"):
+                    tls.sessions = {}
+                    with lock:
+                        parked.append(tls.sessions)
+                return i, run(i, tls.sessions)
+
+            with ThreadPoolExecutor(max_workers=int(workers)) as pool:
+                for i, res in pool.map(worker, order):
+                    record(i, res)
     finally:
-        for sess in sessions.values():
-            sess.close()
+        for sessions in parked:
+            for sess in sessions.values():
+                sess.close()
     results = [done[i] for i in range(len(combos))]
     best = Metrics.default()
     for r, combo in zip(results, combos):

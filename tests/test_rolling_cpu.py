@@ -154,6 +154,29 @@ def test_grid_search_shares_the_resident_copy(monkeypatch, capsys):
     assert [r["kws"]["lambdaAR"] for r in res] == [5.0, 5.0, 5.0, 5.0, 50.0, 50.0, 50.0, 50.0]
 
 
+def test_grid_search_workers_host_logic(monkeypatch, capsys, tmp_path):
+    """grid_search(workers=n): grid points run on a thread pool, one set of parked sessions per worker thread; the results, their
+    order, the best point, the print-out and the pickle are those of the serial run (oracle-backed stand-in session, no device)."""
+    import pickle
+    Y = series(110, 6, seed=3)
+    monkeypatch.setattr(tmod, "train", oracle_train)
+    monkeypatch.setattr(smod, "RollingSession", FakeRollingSession)
+    grid = {"lambdaAR": [5.0, 50.0], "lambdaI": [0.5, 2.0], "k": [2, 3], "window_size": [4, 5]}
+    kw = dict(nr_windows=2, max_iter=2, missing=True)
+    res, best = trmf.grid_search(Y, [1, 2], grid, resident=True, **kw)
+    out = capsys.readouterr().out
+    FakeRollingSession.log = []
+    pkl = tmp_path / "grid.pkl"
+    res3, best3 = trmf.grid_search(Y, [1, 2], grid, resident=True, workers=3, pkl_file=str(pkl), **kw)
+    out3 = capsys.readouterr().out
+    assert len(res3) == 16 and [r["kws"] for r in res] == [r["kws"] for r in res3]
+    assert [r["metrics"] for r in res] == [r["metrics"] for r in res3] and best == best3 and out == out3
+    creates = [e for e in FakeRollingSession.log if e[0] == "create"]
+    assert 4 <= len(creates) <= 12       # 4 session keys (k x window_size), opened by at most 3 workers each
+    with open(pkl, "rb") as fh:
+        assert [r["metrics"] for r in pickle.load(fh)] == [r["metrics"] for r in res]
+
+
 def test_resident_default_and_switches(monkeypatch):
     calls = []
     monkeypatch.setattr(tmod, "_rolling_resident", lambda *a, **k: calls.append("resident") or trmf.Metrics.default())

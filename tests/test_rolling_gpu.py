@@ -159,6 +159,26 @@ def test_grid_search_over_one_resident_copy():
     assert len({r["metrics"].nd for r in res}) == 4          # the weights did reach the device
 
 
+def test_grid_search_with_concurrent_workers_gives_the_serial_results(capsys):
+    """grid_search(workers=3): grid points train at the same time on their own resident sessions / CUDA streams; every point's
+    metrics, the order of the results, the best point and the print-out are the serial run's (a grid in k, the weights and
+    window_size, so workers also open and retire sessions of different keys)."""
+    import time
+    Y = series(600, 60, seed=21).astype(np.float32)
+    grid = {"k": [4, 8], "lambdaAR": [5.0, 50.0, 500.0], "lambdaI": [0.5, 2.0], "window_size": [8, 12]}
+    kw = dict(nr_windows=3, max_iter=6, missing=False, transform=True, lambdaLag=0.5)
+    t0 = time.perf_counter()
+    res1, best1 = trmf.grid_search(Y, [1, 2, 12], grid, workers=1, **kw)
+    t1 = time.perf_counter()
+    out1 = capsys.readouterr().out
+    res3, best3 = trmf.grid_search(Y, [1, 2, 12], grid, workers=3, **kw)
+    t2 = time.perf_counter()
+    out3 = capsys.readouterr().out
+    assert [r["kws"] for r in res1] == [r["kws"] for r in res3] and len(res1) == 24
+    assert [r["metrics"] for r in res1] == [r["metrics"] for r in res3] and best1 == best3 and out1 == out3
+    print("grid_search 24 points: serial {:.3f} s, 3 workers {:.3f} s".format(t1 - t0, t2 - t1))
+
+
 def test_grid_search_matches_the_oracle_loop(monkeypatch, capsys):
     """grid_search (reference trmf.py:331-346) over a grid in k, window_size and the weights -- resident sessions shared where
     the key allows, reordered internally -- against the reference's own loop order with the NumPy oracle doing every fit
