@@ -3,11 +3,11 @@
 //
 // Replaces the hot loop of l2r_ls_pY_IX_chol::solve (reference trmf.cpp:382-395) and, in MODE_GRAD, arr_ls_pY_IX::fun / ::grad
 // (trmf.cpp:231-267), like f_update_mma.cuh -- same decomposition (CTA = NW warps on one series, tiles of 16 entries dealt
-// round-robin to the warps, per-warp cp.async double buffer, fp32 partial sums flushed to per-warp fp64 partials every 128
+// round-robin to the warps, per-warp cp.async double buffer, fp32 partial sums flushed to per-warp fp64 partials every 256
 // entries, deterministic warp-order reduction, deferred fp64 Cholesky), same accuracy construction (exact per-column
 // power-of-two scaling, x = h1 + h2 in fp16, products h2 h1 + h1 h2 + h1 h1 with the small terms first, the truncating
 // tensor-core adder trusted with one tile only).  What changed is everything that was NOT an HMMA in the first kernel
-// (profiles/r01_f_update_mma_k40_sass_mix.txt: 27 HMMA = 216 issue clocks of 620 per tile, ~360 other instructions):
+// (profiles/r01_f_update_mma_k40_sass_mix.txt: 27 HMMA = 216 issue clocks of 620 per tile, ~320 other instructions):
 //
 //  * the fp32 -> (h1, h2) split leaves the hot loop: rows are gathered as [h1[0..8NC) | h2[0..8NC)] fp16 (same bytes per row as
 //    fp32 when 8 | k), written by presplit_kernel together with the scaling -- no F2FP / HADD2.F32 / FADD per tile;
@@ -15,12 +15,14 @@
 //    HMMA wants -- no LDS per value, no register moves between the two homes (both arrangements are loaded; shared memory
 //    has the bandwidth, the issue port does not);
 //  * the right-hand side sum_e y_e x_e rides on the tensor core too: one extra 8-wide B tile per 16-row group whose columns
-//    0 / 1 are the fp16 pair (y1, y2) of the tile's Y values (or, MODE_GRAD, of the residuals), scaled per tile by an exact
-//    power of two taken from the tile's largest magnitude and undone in the fp32 accumulate (an FFMA in place of an FADD);
+//    0 / 1 are the fp16 pair (y1, y2) of the tile's weights.  F-update: pre-split once per Y with one exact global power-of-two
+//    scale (ysplit_kernel).  MODE_GRAD / MODE_STORE: split per tile with an exact power of two taken from the tile's largest
+//    magnitude and undone in the fp32 accumulate (an FFMA in place of an FADD);
+//  * MODE_GONLY: no weights at all -- the Gram over the MISSING cells of a mostly observed Y (complement.cuh);
 //  * MODE_GRAD: z_e = <w_j, x_e> is an HMMA chain over the same staged rows read un-transposed (entries as M, latent index as
 //    the contraction), against a per-series B fragment of the point (w1 | w2), instead of 20 FFMA + 12 SHFL + 12 FADD.
 //
-// Per tile at k = 40: 33 HMMA + ~150 other instructions (MODE_DEFER) against 27 + ~360.
+// Per tile at k = 40: 33 HMMA + ~125 other instructions (MODE_DEFER) against 27 + ~320; 504 against 620 clk (profiles/r02_mma2_history.md).
 #pragma once
 #include <cuda_fp16.h>
 #include <type_traits>
@@ -95,11 +97,7 @@ __global__ void presplit_kernel(const float *__restrict__ X, size_t rows, int k,
 }
 
 __device__ __forceinline__ void cp_async16_s(unsigned smem_addr, const void *gmem) {
-#ifdef FM2_CP_CA
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
-#else
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
-#endif
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");     // (.ca measured slower: profiles/r02_mma2_history.md)
 }
 __device__ __forceinline__ void ldsm_x4_t(uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3, unsigned a) {
     asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a) : "memory");

@@ -5,6 +5,7 @@
 #
 # quick (default, ~4 min): GPU test suite, smoke, bench lines for C2 / C3 (with parity, roofline_x, strong C5 record), reference arm,
 #                          rolling_validate runs, ncu launch list of the bench command.
+# ncu:                     only what `full` adds.
 # full  (+ ~4 min):        also the ncu --set full captures (the kernels of one outer iteration of the default path: complement
 #                          Gram, fp64 product, solve, Gram assembly; and the two Gram launches of the walk over Omega with
 #                          TRMF_B200_COMPLEMENT=0), the standalone kernel test, the walk-path bench line and the C4 line.
@@ -17,6 +18,7 @@ out=gpurun_out
 mkdir -p "$out"
 run() { local name="$1"; shift; echo "== $name: $*"; ( time timeout "${TMO:-300}" "$@" ) > "$out/$name.log" 2>&1; tail -4 "$out/$name.log"; }
 
+if [ "$mode" != "ncu" ]; then
 TMO=900 run ${tag}_gpu_tests python -m pytest tests -m gpu -q -x --durations=8
 TMO=120 run ${tag}_smoke python -c "import __graft_entry__ as g; g.smoke()"
 timeout 400 python bench.py > "$out/${tag}_bench_c2_n1.json" 2> "$out/${tag}_bench_c2_n1.err"; cut -c1-300 "$out/${tag}_bench_c2_n1.json"
@@ -28,12 +30,16 @@ done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$out/${tag}_launches_c2.csv" \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_launches.log" 2>&1
 python tools/ncu_summary.py "$out/${tag}_launches_c2.csv" > "$out/${tag}_launches_c2.txt"; head -14 "$out/${tag}_launches_c2.txt"
+fi
 
-if [ "$mode" = "full" ]; then
+if [ "$mode" = "full" ] || [ "$mode" = "ncu" ]; then
     timeout 500 ncu --set full --clock-control none --import-source on -k 'regex:gemm64|f_update_mma2|solve_kernel|xgram_kernel' -s 6 -c 6 \
         -o "$out/${tag}_complement_full" -f python bench.py --steps 1 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_full.log" 2>&1
+    # (the reports are turned into text here: gpurun brings back at most 64 MiB)
+    python tools/ncu_kernel_report.py "$out/${tag}_complement_full.ncu-rep" > "$out/${tag}_complement_ncu_full.txt" 2>&1; rm -f "$out/${tag}_complement_full.ncu-rep"
     TRMF_B200_COMPLEMENT=0 timeout 500 ncu --set full --clock-control none --import-source on -k regex:f_update_mma2 -s 2 -c 2 \
         -o "$out/${tag}_mma2_k40_full" -f python bench.py --steps 1 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_full2.log" 2>&1
+    python tools/ncu_kernel_report.py "$out/${tag}_mma2_k40_full.ncu-rep" > "$out/${tag}_mma2_k40_ncu_full.txt" 2>&1; rm -f "$out/${tag}_mma2_k40_full.ncu-rep"
     TRMF_B200_COMPLEMENT=0 timeout 400 python bench.py --strong none --no-cpu-baseline > "$out/${tag}_bench_c2_n1_walk.json" 2> "$out/${tag}_bench_c2_n1_walk.err"
     for a in "40 small" "64 small" "20 small" "40 c2" "64 c5"; do echo "=== $a"; timeout 120 tools/test_f_update_mma2 $a 2>&1 | tail -8; done > "$out/${tag}_test_f_update_mma2.txt" 2>&1
     tools/microbench_dfma > "$out/${tag}_microbench_dfma.txt" 2>&1
