@@ -464,13 +464,14 @@ def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
     launches0 = s.stat("kernel_launches")
     coll0 = s.stat("collectives")
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    fk_ms, f_ms, x_ms, lag_ms, cg, xg_ms = [], [], [], [], [], []
+    fk_ms, f_ms, x_ms, lag_ms, cg, xg_ms, cmg_ms, cmp_ms = [], [], [], [], [], [], [], []
     with torch.cuda.stream(stream):
         e0.record(stream)
         for _ in range(args.steps):
             step()
             fk_ms.append(s.stat("f_kernel_ms")); f_ms.append(s.stat("f_ms")); x_ms.append(s.stat("x_ms"))
             lag_ms.append(s.stat("lag_ms")); cg.append(int(s.stat("cg_iters"))); xg_ms.append(s.stat("x_gram_ms"))
+            cmg_ms.append(s.stat("cm_gram_ms")); cmp_ms.append(s.stat("cm_product_ms"))
         e1.record(stream)
     barrier()
     clocks = sampler.stop() if (rank == 0 and not light) else None
@@ -493,27 +494,63 @@ def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
     achieved = bytes_f / (fk * 1e-3) / 1e9
     flops_f = nnz_loc * (k * k + 3 * k) + n_loc * (k ** 3 / 3 + 2 * k * k)
     compl = s.stat("formulation") > 0
-    COMPL_NOTE = ("complement formulation (csrc/complement.cuh): Y observes >= 70 % of its cells, so the Gram is X^T X minus a gather over the "
-                  "MISSING cells and the right-hand sides are one fp64 tall-skinny product over the zero-filled dense Y; `achieved` keeps "
-                  "SURVEY 8d's per-observed-entry gather model, which this formulation no longer moves -- a fraction above 1 is the algorithm, "
-                  "not the memory system (DRAM traffic per launch is in `traffic`); the dominant kernel is the DFMA-bound product, see "
-                  "profiles/r02_launches_c2.txt")
     roofline = {"bound": "hbm", "kernel": "f_update (Gram + Cholesky per series)", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(cfg_key, k, world), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_f, "kernel_ms": fk, "fp32_tflops": flops_f / (fk * 1e-3) / 1e12,
-                "entries_per_s": nnz_loc / (fk * 1e-3), "formulation": "complement" if compl else "walk over the observed entries"}
+                "entries_per_s": nnz_loc / (fk * 1e-3), "formulation": "walk over the observed entries"}
     if compl:
-        roofline["note"] = COMPL_NOTE
+        # Complement formulation (csrc/complement.cuh): Y observes >= 70 % of its cells, so the Gram of a series is W^T W minus a
+        # gather over its MISSING time stamps and the right-hand sides are one fp64 tall-skinny product over the zero-filled dense
+        # Y.  SURVEY 8d's per-observed-entry bytes are no longer what the F-update moves; the roofline is stated for the two
+        # kernels it now consists of, each under the model that bounds it:
+        #   roofline         the gather kernel (fm::f_update_mma2_kernel<MODE_GONLY>) over the missing cells, SURVEY 8d's gather
+        #                    model per walked cell: 4 B index + 4k B factor row, + 8 B of row pointer per series  -> HBM figure
+        #   roofline_product cm::gemm64_partial_kernel, 2 T n k fp64 flops on the DMMA path against the measured DMMA issue rate
+        #                    (tools/microbench_dfma.cu -> profiles/r02_microbench_dfma.txt); its bytes (T n fp32 once) are a
+        #                    small fraction of HBM, stated beside it
+        nmiss = float(s.stat("cm_missing"))
+        g_ms, p_ms = float(np.mean(cmg_ms)), float(np.mean(cmp_ms))
+        bytes_g = nmiss * (4 + 4 * k) + n_loc * 8
+        roofline = {"bound": "hbm", "kernel": "fm::f_update_mma2_kernel<MODE_GONLY>: per-series Gram over the MISSING cells (F-update, complement formulation)",
+                    "achieved": bytes_g / (g_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_g / (g_ms * 1e-3) / 1e9 / peak,
+                    "traffic": ncu_traffic(cfg_key, k, world, "cm_gram"), "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bytes_g, "kernel_ms": g_ms, "cells_walked": nmiss,
+                    "cells_per_s": nmiss / (g_ms * 1e-3), "formulation": "complement",
+                    "f_update_ms": fk, "f_update_observed_entries_per_s": nnz_loc / (fk * 1e-3),
+                    "f_update_equivalent_walk_gbs": achieved,
+                    "note": "kernel_ms = CUDA events around the factor pre-split + the gather kernel of the last whole-Y F-update; "
+                            "f_update_equivalent_walk_gbs is what SURVEY 8d's per-OBSERVED-entry model would read for the whole F-update "
+                            "(above the HBM figure: the formulation does not move those bytes, it is not a bandwidth claim)"}
+        DMMA_PEAK_TFLOPS = 2 * 18.5      # mma.sync.m8n8k4.f64: 18.5 TMAC/s measured (profiles/r02_microbench_dfma.txt)
+        flops_p = 2.0 * T * n_loc * k
+        roofline_product = {"bound": "tensor", "kernel": "cm::gemm64_partial_kernel: right-hand sides Y0^T W in fp64 (DMMA) + split-K finish",
+                            "achieved": flops_p / (p_ms * 1e-3) / 1e12, "peak": DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                            "frac": flops_p / (p_ms * 1e-3) / 1e12 / DMMA_PEAK_TFLOPS, "traffic": ncu_traffic(cfg_key, k, world, "cm_product"),
+                            "peak_source": "fp64 DMMA issue rate measured by tools/microbench_dfma.cu (profiles/r02_microbench_dfma.txt); "
+                                           "MEASURED_PEAKS.json has no fp64 figure",
+                            "algorithmic_flops_per_launch": flops_p, "algorithmic_bytes_per_launch": 4.0 * T * n_loc + 4.0 * T * k + 8.0 * n_loc * k,
+                            "hbm_frac": (4.0 * T * n_loc + 4.0 * T * k + 8.0 * n_loc * k) / (p_ms * 1e-3) / 1e9 / peak, "kernel_ms": p_ms}
+    else:
+        roofline_product = None
     # ---- second roofline: the X-update's Gram build with the fused loss value / gradient (rows = time stamps).
     # Algorithmic bytes: the same gather model, N(8+4k) + T(8+4k), plus the T k^2 fp32 Grams it stores.
     xg = float(np.mean(xg_ms)) if xg_ms and np.mean(xg_ms) > 0 else None
     roofline_x = None
-    if xg:
+    if xg and compl:
+        # the complement formulation's Gram build as a whole (gather over the missing cells by time stamp + fp64 product Y0 H +
+        # assembly of Gram / gradient / objective): bytes it has to move = walked cells + the dense Y once + the Grams it stores
+        bytes_x = nmiss * (4 + 4 * k) + T * 8 + 4.0 * T * n_loc + T * k * k * 4
+        roofline_x = {"bound": "hbm", "kernel": "x_update Gram build, complement formulation (gather over missing cells + fp64 product + assembly; 3 kernels)",
+                      "achieved": bytes_x / (xg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": bytes_x / (xg * 1e-3) / 1e9 / peak,
+                      "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_x, "kernel_ms": xg,
+                      "observed_entries_per_s": nnz_loc / (xg * 1e-3), "formulation": "complement",
+                      "note": "the fp64 product inside it is DMMA-issue bound (roofline_product), not HBM bound"}
+    elif xg:
         bytes_x = nnz_loc * (8 + 4 * k) + T * (8 + 4 * k) + T * k * k * 4
         roofline_x = {"bound": "hbm", "kernel": "x_update Gram build + fused fun/grad (per time stamp)", "achieved": bytes_x / (xg * 1e-3) / 1e9,
                       "peak": peak, "unit": "GB/s", "frac": bytes_x / (xg * 1e-3) / 1e9 / peak, "traffic": ncu_traffic(cfg_key, k, world, "x_gram"),
                       "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_x, "kernel_ms": xg,
-                      "entries_per_s": nnz_loc / (xg * 1e-3), "formulation": "complement" if compl else "walk over the observed entries"}
+                      "entries_per_s": nnz_loc / (xg * 1e-3), "formulation": "walk over the observed entries"}
 
     # ---- end to end through the public host-buffer API ----
     e2e = None if (args.no_e2e or light) else run_e2e(args, cfg, torch, dist, lib, s, sd, dtype, rank, world, local_rank, lags, W0, H0, L0,
@@ -539,7 +576,7 @@ def run_b200_arm(args, cfg, rank, world, local_rank, cfg_key, light=False):
                            "l2": "inputs larger than L2 (Y = {:.2f} GB per GPU in two orientations); no flush".format(nnz_loc * 16 / 1e9),
                            "step": "one outer iteration F->X->lag_val restarted from the same factors"},
                 "e2e": e2e, "gpu_launches": launches, "collectives": collectives, "clocks": clocks, "roofline": roofline,
-                "roofline_x": roofline_x, "parity": parity,
+                "roofline_x": roofline_x, "roofline_product": roofline_product, "parity": parity,
                 "phase_ms": {"f_update": float(np.mean(f_ms)), "x_update": float(np.mean(x_ms)), "lag_update": float(np.mean(lag_ms))},
                 "cg_steps": cg}
     return line

@@ -154,6 +154,101 @@ __device__ __forceinline__ void block_chol_solve_blocked(double *A, int ld, doub
     __syncthreads();
 }
 
+// One-warp variant on PACKED lower-triangular storage: row i (i = 0..n, row n = right-hand side, n entries) starts at i (i + 1) / 2.
+// Same panels, same arithmetic in the same order as block_chol_solve_blocked -- bit-identical factors -- but half the shared memory
+// per system and no CTA barrier: the deferred solve kernels run one system per warp and keep 2-4x as many systems in flight per SM
+// (the factorisation is a chain of short dependent steps; with 128 threads per system ncu showed 50 % barrier stalls and 43k clk
+// per 40 x 40 system at 6 systems per SM).  Called by all 32 lanes of one warp; n + 1 <= 32 * SLOTS.
+__device__ __forceinline__ int tri_off(int i) { return (i * (i + 1)) >> 1; }
+template <int SLOTS>
+__device__ __forceinline__ void warp_chol_solve_packed(double *A, double *dinv, int n) {
+    const int lane = threadIdx.x & 31;
+    const int tx = lane & 15, ty = lane >> 4;
+    for (int c0 = 0; c0 < n; c0 += 8) {
+        const int w = n - c0 < 8 ? n - c0 : 8;
+        __syncwarp();   // trailing update of the previous panel finished
+        {
+            double p[SLOTS][8];
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int row = c0 + lane + 32 * s;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) p[s][q] = (row <= n && q < w && c0 + q <= row) ? A[tri_off(row) + c0 + q] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < w) {
+                    const double d = __shfl_sync(FULL_MASK, p[0][q], q);      // pivot A[c][c], c = c0 + q
+                    const double inv = rsqrt(d);
+                    if (lane == 0) dinv[c0 + q] = inv;
+#pragma unroll
+                    for (int s = 0; s < SLOTS; ++s)
+                        if (lane + 32 * s > q) p[s][q] *= inv;                 // rows below the pivot: L[i][c]
+#pragma unroll
+                    for (int q2 = q + 1; q2 < 8; ++q2) {
+                        const double lj = __shfl_sync(FULL_MASK, p[0][q], q2);  // L[c0+q2][c]
+#pragma unroll
+                        for (int s = 0; s < SLOTS; ++s)
+                            if (lane + 32 * s >= q2) p[s][q2] -= p[s][q] * lj; // lower part of panel column q2
+                    }
+                }
+            }
+#pragma unroll
+            for (int s = 0; s < SLOTS; ++s) {
+                const int row = c0 + lane + 32 * s;
+                if (row <= n) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        if (q < w && lane + 32 * s > q) A[tri_off(row) + c0 + q] = p[s][q];
+                }
+            }
+        }
+        __syncwarp();
+        // trailing update: A[i][j] -= sum_q L[i][c0+q] L[j][c0+q]   (i in (c0+w .. n], j in [c0+w .. min(i, n-1)])
+        const int t0 = c0 + w;
+        for (int i = t0 + ty; i <= n; i += 2) {
+            const double *ri = A + tri_off(i);
+            double li[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) li[q] = q < w ? ri[c0 + q] : 0.0;
+            const int jmax = i < n ? i : n - 1;
+            for (int j = t0 + tx; j <= jmax; j += 16) {
+                const double *rj = A + tri_off(j);
+                double acc = ri[j];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc -= li[q] * (q < w ? rj[c0 + q] : 0.0);
+                A[tri_off(i) + j] = acc;
+            }
+        }
+    }
+    __syncwarp();
+    // backward substitution L^T x = y; lane owns x[lane + 32 q]
+    {
+        double y[SLOTS];
+        const int rn = tri_off(n);
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) { const int i = lane + 32 * q; y[q] = i < n ? A[rn + i] : 0.0; }
+        for (int c = n - 1; c >= 0; --c) {
+            const int q = c >> 5, owner = c & 31;
+            double v = y[0];
+#pragma unroll
+            for (int qq = 1; qq < SLOTS; ++qq) v = q == qq ? y[qq] : v;
+            v *= dinv[c];
+            v = __shfl_sync(FULL_MASK, v, owner);
+            const double *rc = A + tri_off(c);
+#pragma unroll
+            for (int qq = 0; qq < SLOTS; ++qq) {
+                const int i = lane + 32 * qq;
+                if (i == c) y[qq] = v;
+                else if (i < c) y[qq] -= rc[i] * v;
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < SLOTS; ++q) { const int i = lane + 32 * q; if (i < n) A[rn + i] = y[q]; }
+    }
+    __syncwarp();
+}
+
 // Cholesky solve of an SPD system held in shared memory, by the whole CTA.
 //
 // Layout: `A` has n+1 rows of leading dimension ld (row-major, fp64).  Rows

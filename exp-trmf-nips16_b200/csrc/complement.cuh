@@ -57,26 +57,63 @@ __global__ void missing_bitmap_kernel(const uint64_t *__restrict__ ptr, const ui
     }
 }
 
-// Y0[t * n + j] = Y_tj at the observed cells (the buffer is zeroed first); from the by-time CSR, so a row's stores are nearly contiguous
-__global__ void scatter_dense_kernel(const uint64_t *__restrict__ row_ptr, const uint32_t *__restrict__ col_idx, const float *__restrict__ val_t,
-                                     uint64_t T, uint64_t n, float *__restrict__ Y0) {
-    const int lane = threadIdx.x & 31;
-    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
-    for (uint64_t t = warp; t < T; t += nwarps) {
-        const uint64_t e0 = row_ptr[t], e1 = row_ptr[t + 1];
-        float *row = Y0 + t * n;
-        for (uint64_t e = e0 + lane; e < e1; e += 32) row[col_idx[e]] = val_t[e];
-    }
+// Y0[t * n + j] = Y_tj at the observed cells of the series [0, nseries) behind `col_ptr` (the buffer is zeroed first); from the
+// by-series CSC, so that a series slab can be placed the moment it has landed.  A thread walks one of SC_CHUNKS pieces of one series
+// (its reads run along the series and stay in L1); the 32 lanes of a warp hold the same piece of 32 neighbouring series and, Y being
+// mostly observed, sit on nearly the same time stamp, so a warp's stores fall into a few 128-byte lines of Y0 and the partial
+// sectors merge in L2.  Block = (32, 8), grid = (ceil(nseries / 32), SC_CHUNKS / 8).
+constexpr int SC_CHUNKS = 32;
+__global__ void scatter_dense_csc_kernel(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ row_idx, const float *__restrict__ val,
+                                         uint64_t nseries, uint64_t n, float *__restrict__ Y0col) {
+    const uint64_t j = blockIdx.x * 32ull + threadIdx.x;
+    if (j >= nseries) return;
+    const uint64_t c = blockIdx.y * (uint64_t)blockDim.y + threadIdx.y;
+    const uint64_t p0 = col_ptr[j], len = col_ptr[j + 1] - p0;
+    const uint64_t e0 = p0 + len * c / SC_CHUNKS, e1 = p0 + len * (c + 1) / SC_CHUNKS;
+    float *col = Y0col + j;
+#pragma unroll 4
+    for (uint64_t e = e0; e < e1; ++e) col[(uint64_t)row_idx[e] * n] = val[e];
 }
-// yy[t] = sum of squares of row t's values (fp64; one warp per row, fixed order)
-__global__ void row_sumsq_kernel(const uint64_t *__restrict__ row_ptr, const float *__restrict__ val_t, uint64_t T, double *__restrict__ yy) {
+// yy[t] = sum of squares of row t of Y0 (= of the observed values of time stamp t: the zero-filled cells add nothing); fp64, one warp
+// per row, fixed order
+__global__ void row_sumsq_dense_kernel(const float *__restrict__ Y0, uint64_t T, uint64_t n, double *__restrict__ yy) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
     for (uint64_t t = warp; t < T; t += nwarps) {
+        const float *row = Y0 + t * n;
         double a = 0.0;
-        for (uint64_t e = row_ptr[t] + lane; e < row_ptr[t + 1]; e += 32) a += (double)val_t[e] * (double)val_t[e];
+        for (uint64_t j = lane; j < n; j += 32) { const double v = (double)row[j]; a += v * v; }
         a = warp_sum(a);
         if (lane == 0) yy[t] = a;
+    }
+}
+// the by-series list of missing cells, transposed into one bitmap per time stamp: bit j of bmT[t] is set iff (t, j) is missing.
+// atomicOr: the result does not depend on the order, and series slabs can add their bits as they arrive.  `j0` = index of the
+// first series behind cptr.
+__global__ void transpose_missing_kernel(const uint64_t *__restrict__ cptr, const uint32_t *__restrict__ cidx, uint64_t nseries, uint64_t j0,
+                                         uint32_t words, uint32_t *__restrict__ bmT) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t jj = warp; jj < nseries; jj += nwarps) {
+        const uint64_t j = j0 + jj, e1 = cptr[jj + 1];
+        const uint32_t bit = 1u << (j & 31);
+        for (uint64_t e = cptr[jj] + lane; e < e1; e += 32) atomicOr(bmT + (uint64_t)cidx[e] * words + (j >> 5), bit);
+    }
+}
+// cnt[r] = set bits of row r's bitmap among the first `dim` (cnt[rows] = 0: the scan's total lands there)
+__global__ void count_bits_kernel(const uint32_t *__restrict__ bm, uint64_t rows, uint64_t dim, uint32_t words, uint64_t *__restrict__ cnt) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5, nwarps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t r = warp; r <= rows; r += nwarps) {
+        uint32_t c = 0;
+        if (r < rows)
+            for (uint32_t w = lane; w < words; w += 32) {
+                uint32_t bits = bm[r * (uint64_t)words + w];
+                if (w == words - 1 && (dim & 31)) bits &= (1u << (dim & 31)) - 1u;
+                c += __popc(bits);
+            }
+        c = __reduce_add_sync(FULL_MASK, c);
+        if (lane == 0) cnt[r] = c;
     }
 }
 
@@ -195,8 +232,11 @@ template <int NB> constexpr size_t gemm64_smem() { return sizeof(double) * ((siz
 // ---- F-update: (X^T X - Gmiss_j + lambda I) f = rhs_j, one CTA per system at a time (fp64 Cholesky of common.cuh) ----
 // sys[j] = the (K+1) x (K+1) lower-triangle layout MODE_GONLY leaves (only read when the series has missing cells), XtX = K x K fp64
 // (full), rhs = n x K fp64.  A series without any observation keeps its row (trmf.cpp:374).
-template <int K>
-__global__ void __launch_bounds__(128)
+// NT threads per system: the factorisation is a chain of short dependent steps (panel by warp 0, barrier, trailing update, barrier),
+// so a CTA of 128 spends half its time at barriers (ncu: 50 % barrier stalls, 43k clk per 40 x 40 system); fewer threads per
+// system and more systems in flight per SM is the better trade -- NT is chosen by the launcher (TRMF_B200_SOLVE_THREADS pins it).
+template <int K, int NT>
+__global__ void __launch_bounds__(NT)
 solve_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ XtX,
              const double *__restrict__ rhs, float *__restrict__ F, double lambda, uint32_t nseries) {
     constexpr int ld = K + 1;
@@ -208,16 +248,49 @@ solve_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr
         if (ptr[j + 1] == ptr[j]) continue;
         const bool miss = cptr[j + 1] != cptr[j];
         const double *src = sys + (size_t)j * ((K + 1) * ld);
-        for (int p = tid; p < K * K; p += 128) {
+        for (int p = tid; p < K * K; p += NT) {
             const int r = p / K, c = p - r * K;
             if (c <= r) A[r * ld + c] = XtX[p] - (miss ? src[r * ld + c] : 0.0);
         }
-        if (tid < K) A[K * ld + tid] = rhs[(size_t)j * K + tid];
+        for (int c = tid; c < K; c += NT) A[K * ld + c] = rhs[(size_t)j * K + c];
         __syncthreads();
-        if (tid < K) A[tid * ld + tid] += lambda;       // trmf.cpp:393
+        for (int c = tid; c < K; c += NT) A[c * ld + c] += lambda;       // trmf.cpp:393
         block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, K);   // starts and ends with __syncthreads
-        if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
+        for (int c = tid; c < K; c += NT) F[(size_t)j * K + c] = (float)A[K * ld + c];
         __syncthreads();
+    }
+}
+
+// One warp per system on packed triangular storage (warp_chol_solve_packed, common.cuh): the default.  CTA = 32 threads.
+template <int K> constexpr size_t solve_warp_smem() { return sizeof(double) * ((size_t)K * (K + 1) / 2 + K + K); }
+template <int K>
+__global__ void __launch_bounds__(32)
+solve_warp_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ XtX,
+                  const double *__restrict__ rhs, float *__restrict__ F, double lambda, uint32_t nseries) {
+    constexpr int ld = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A = reinterpret_cast<double *>(smem_raw);
+    double *dinv = A + (K * (K + 1) / 2 + K);
+    const int lane = threadIdx.x;
+    for (uint32_t j = blockIdx.x; j < nseries; j += gridDim.x) {
+        if (ptr[j + 1] == ptr[j]) continue;
+        const bool miss = cptr[j + 1] != cptr[j];
+        const double *src = sys + (size_t)j * ((K + 1) * ld);
+        // (one flat, unrolled loop over the square: the loads of several steps are in flight together; a loop per row would pay a
+        //  global-memory round trip per row)
+#pragma unroll 4
+        for (int p = lane; p < K * K; p += 32) {
+            const int r = p / K, c = p - r * K;
+            if (c <= r) {
+                double v = XtX[p] - (miss ? src[r * ld + c] : 0.0);
+                if (c == r) v += lambda;       // trmf.cpp:393
+                A[tri_off(r) + c] = v;
+            }
+        }
+        for (int c = lane; c < K; c += 32) A[tri_off(K) + c] = rhs[(size_t)j * K + c];
+        warp_chol_solve_packed<(K + 32) / 32>(A, dinv, K);   // starts and ends with __syncwarp
+        for (int c = lane; c < K; c += 32) F[(size_t)j * K + c] = (float)A[tri_off(K) + c];
+        __syncwarp();
     }
 }
 
@@ -226,7 +299,7 @@ solve_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr
 // A time stamp without observations: zero Gram, frow 0, gradient row untouched (gaccum) or zero -- as the walk leaves it.
 template <int K>
 __global__ void __launch_bounds__(128)
-xgram_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ HtH,
+xgram_kernel(uint64_t dim, const uint64_t *__restrict__ cptr, const double *__restrict__ sys, const double *__restrict__ HtH,
              const double *__restrict__ rhs, const double *__restrict__ yy, const float *__restrict__ Wv, float *__restrict__ F,
              float *__restrict__ Gout, int gaccum, double *__restrict__ frow, uint32_t nrows) {
     constexpr int ld = K + 1;
@@ -236,7 +309,7 @@ xgram_kernel(const uint64_t *__restrict__ ptr, const uint64_t *__restrict__ cptr
     const int tid = threadIdx.x;
     for (uint32_t t = blockIdx.x; t < nrows; t += gridDim.x) {
         float *Gt = Gout + (size_t)t * K * K;
-        if (ptr[t + 1] == ptr[t]) {
+        if (cptr[t + 1] - cptr[t] == dim) {      // no observation at this time stamp
             for (int p = tid; p < K * K; p += 128) Gt[p] = 0.f;
             if (tid == 0) frow[t] = 0.0;
             if (!gaccum && tid < K) F[(size_t)t * K + tid] = 0.f;

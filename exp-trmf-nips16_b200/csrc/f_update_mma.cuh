@@ -443,8 +443,10 @@ f_update_mma_kernel(const uint64_t *__restrict__ ptr, const uint32_t *__restrict
 
 // The solve of MODE_DEFER: one CTA per system at a time, many CTAs per SM.  Same arithmetic as the in-kernel solve
 // (block_chol_solve_blocked does not depend on the block size), so the factors are bit-identical either way.
-template <int K>
-__global__ void __launch_bounds__(128)
+// NTH threads per system (32 / 64 / 128, chosen by the launcher): see cm::solve_kernel -- the factorisation is a chain of short
+// dependent steps, more systems in flight per SM beat more threads per system.
+template <int K, int NTH>
+__global__ void __launch_bounds__(NTH)
 chol_solve_kernel(const uint64_t *__restrict__ ptr, const double *__restrict__ sys, float *__restrict__ F, double lambda,
                   uint32_t nseries) {
     constexpr int ld = K + 1;
@@ -455,12 +457,36 @@ chol_solve_kernel(const uint64_t *__restrict__ ptr, const double *__restrict__ s
     for (uint32_t j = blockIdx.x; j < nseries; j += gridDim.x) {
         if (ptr[j + 1] == ptr[j]) continue;             // no observation: the row keeps its value (trmf.cpp:374)
         const double *src = sys + (size_t)j * ((K + 1) * ld);
-        for (int p = tid; p < (K + 1) * ld; p += 128) A[p] = src[p];
+        for (int p = tid; p < (K + 1) * ld; p += NTH) A[p] = src[p];
         __syncthreads();
-        if (tid < K) A[tid * ld + tid] += lambda;       // trmf.cpp:393
+        for (int c = tid; c < K; c += NTH) A[c * ld + c] += lambda;       // trmf.cpp:393
         block_chol_solve_blocked<(K + 32) / 32>(A, ld, dinv, K);   // starts and ends with __syncthreads
-        if (tid < K) F[(size_t)j * K + tid] = (float)A[K * ld + tid];
+        for (int c = tid; c < K; c += NTH) F[(size_t)j * K + c] = (float)A[K * ld + c];
         __syncthreads();
+    }
+}
+
+// One warp per system on packed triangular storage (warp_chol_solve_packed): the default of the deferred solve.
+template <int K>
+__global__ void __launch_bounds__(32)
+chol_solve_warp_kernel(const uint64_t *__restrict__ ptr, const double *__restrict__ sys, float *__restrict__ F, double lambda,
+                       uint32_t nseries) {
+    constexpr int ld = K + 1;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *A = reinterpret_cast<double *>(smem_raw);
+    double *dinv = A + (K * (K + 1) / 2 + K);
+    const int lane = threadIdx.x;
+    for (uint32_t j = blockIdx.x; j < nseries; j += gridDim.x) {
+        if (ptr[j + 1] == ptr[j]) continue;             // no observation: the row keeps its value (trmf.cpp:374)
+        const double *src = sys + (size_t)j * ((K + 1) * ld);
+#pragma unroll 4
+        for (int p = lane; p < (K + 1) * ld; p += 32) {      // (flat and unrolled: several loads in flight)
+            const int r = p / ld, c = p - r * ld;
+            if (c <= r && c < K) A[tri_off(r) + c] = src[p] + (c == r ? lambda : 0.0);   // trmf.cpp:393
+        }
+        warp_chol_solve_packed<(K + 32) / 32>(A, dinv, K);   // starts and ends with __syncwarp
+        for (int c = lane; c < K; c += 32) F[(size_t)j * K + c] = (float)A[tri_off(K) + c];
+        __syncwarp();
     }
 }
 
@@ -480,24 +506,44 @@ static inline size_t f_update_mma_sys_doubles(int k) { return (size_t)(k + 1) * 
 // solve the nseries systems a MODE_DEFER launch left in `sys`
 static inline int f_update_mma_solve(cudaStream_t st, int num_sms, const uint64_t *ptr, const double *sys, V *F, int k, double lambda,
                                      uint32_t nseries, unsigned long long *launches) {
-#define FS_CASE(KK)                                                                                             \
-    case KK: {                                                                                                  \
+#define FS_LAUNCH(KK, NTH)                                                                                      \
+    do {                                                                                                        \
         const size_t smem = sizeof(double) * ((size_t)(KK + 1) * (KK + 1) + KK);                                \
-        auto kfn = fm::chol_solve_kernel<KK>;                                                                   \
+        auto kfn = fm::chol_solve_kernel<KK, NTH>;                                                              \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
         int per_sm = 0;                                                                                         \
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem) != cudaSuccess) return 1;    \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, NTH, smem) != cudaSuccess) return 1;    \
         unsigned grid = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)num_sms;                                \
         if (grid > nseries) grid = nseries;                                                                     \
-        kfn<<<grid ? grid : 1, 128, smem, st>>>(ptr, sys, F, lambda, nseries);                                  \
-        break;                                                                                                  \
-    }
+        kfn<<<grid ? grid : 1, NTH, smem, st>>>(ptr, sys, F, lambda, nseries);                                  \
+    } while (0)
+#define FS_WARP(KK)                                                                                             \
+    do {                                                                                                        \
+        const size_t smem = sizeof(double) * ((size_t)KK * (KK + 1) / 2 + 2 * KK);                              \
+        auto kfn = fm::chol_solve_warp_kernel<KK>;                                                              \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1; \
+        int per_sm = 0;                                                                                         \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 32, smem) != cudaSuccess) return 1;     \
+        unsigned grid = (unsigned)(per_sm > 0 ? per_sm : 1) * (unsigned)num_sms;                                \
+        if (grid > nseries) grid = nseries;                                                                     \
+        kfn<<<grid ? grid : 1, 32, smem, st>>>(ptr, sys, F, lambda, nseries);                                   \
+    } while (0)
+#define FS_CASE(KK)                                                                                             \
+    case KK:                                                                                                    \
+        if (nth == 32) FS_WARP(KK); else if (nth == 64) FS_LAUNCH(KK, 64); else FS_LAUNCH(KK, 128);             \
+        break;
+    // 128 / 64 = one CTA per system, 32 = one warp per system on packed storage.  Measured (F-update, ms): C4 32.33 / 32.48, C5
+    // 186.2 / 184.6 for 128 / 32 -- the solve is not what bounds those F-updates; identical factors either way.
+    int nth = 128;
+    if (const char *e = getenv("TRMF_B200_SOLVE_THREADS")) nth = atoi(e);
     switch (k) {
         FS_CASE(8) FS_CASE(12) FS_CASE(16) FS_CASE(20) FS_CASE(24) FS_CASE(28) FS_CASE(32) FS_CASE(36) FS_CASE(40) FS_CASE(44) FS_CASE(48) FS_CASE(52)
         FS_CASE(56) FS_CASE(60) FS_CASE(64)
         default: return 1;
     }
 #undef FS_CASE
+#undef FS_LAUNCH
+#undef FS_WARP
     ++*launches;
     return cudaGetLastError() != cudaSuccess;
 }

@@ -548,7 +548,7 @@ static inline int f_update_mma2_launch(cudaStream_t st, int num_sms, const uint6
                                        const V *X, size_t xrows, V *Xs, float *invs, V *F, V *Gout, int k, double lambda,
                                        uint32_t nseries, unsigned *queue, unsigned long long *launches,
                                        const V *Wv = nullptr, int gaccum = 0, double *frow = nullptr, bool rescale = true,
-                                       const float *ysc = nullptr, V *Xr = nullptr) {
+                                       const float *ysc = nullptr, V *Xr = nullptr, uint32_t rows_total = 0) {
     if (cudaMemsetAsync(queue, 0, sizeof(unsigned) * (rescale ? 8 + 128 : 1), st) != cudaSuccess) return 1;
     if (rescale) {
         const size_t total = xrows * (size_t)k;
@@ -560,7 +560,9 @@ static inline int f_update_mma2_launch(cudaStream_t st, int num_sms, const uint6
         fm::presplit_kernel<<<g1, 256, sizeof(float) * k, st>>>(X, xrows, k, queue + 8, reinterpret_cast<__half *>(Xs), invs, Xr);
         *launches += 2;
     }
-    const bool wide = nseries < (uint32_t)(24 * num_sms);
+    // (a launch over one range of a longer row list -- rows_total rows in all -- takes the CTA shape the whole list would get: a row's
+    //  sums then do not depend on how the list was cut)
+    const bool wide = (rows_total ? rows_total : nseries) < (uint32_t)(24 * num_sms);
 #define FM2_LAUNCH(KK, NWW, MINBB)                                                                              \
     do {                                                                                                        \
         const size_t smem = fm::Cfg2<KK>::smem(NWW);                                                            \
@@ -595,5 +597,5 @@ static inline int f_update_mma2_split_y(cudaStream_t, int, const V *, const uint
 template <int MODE>
 static inline int f_update_mma2_launch(cudaStream_t, int, const uint64_t *, const uint32_t *, const V *, const V *, size_t, V *, float *,
                                        V *, V *, int, double, uint32_t, unsigned *, unsigned long long *, const V * = nullptr, int = 0,
-                                       double * = nullptr, bool = true, const float * = nullptr, V * = nullptr) { return 1; }
+                                       double * = nullptr, bool = true, const float * = nullptr, V * = nullptr, uint32_t = 0) { return 1; }
 #endif

@@ -67,7 +67,8 @@ __global__ void ingest_rowptr_kernel(const uint32_t *__restrict__ keys, uint64_t
 // TRMF_SPARSE_BITMAP ingest: row_idx[col_ptr[j] ..] = the set bits of series j's bitmap (words = ceil(T / 32) per series), ascending.
 // One warp per series, 32 words per step: popc + warp prefix sum place every lane's bits.  Bit-exact by construction; a bitmap whose
 // population disagrees with col_ptr is clipped to the series' range (never writes outside it).
-__global__ void bitmap_expand_kernel(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ bitmap, uint64_t n, uint64_t T,
+template <bool INVERT>
+__device__ __forceinline__ void bitmap_expand_body(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ bitmap, uint64_t n, uint64_t T,
                                      uint32_t words, uint32_t *__restrict__ row_idx) {
     const int lane = threadIdx.x & 31;
     const uint64_t warp = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5;
@@ -78,7 +79,7 @@ __global__ void bitmap_expand_kernel(const uint64_t *__restrict__ col_ptr, const
         const uint32_t *bm = bitmap + j * (uint64_t)words;
         for (uint32_t w0 = 0; w0 < words; w0 += 32) {
             const uint32_t wi = w0 + lane;
-            uint32_t bits = wi < words ? __ldg(bm + wi) : 0u;
+            uint32_t bits = wi < words ? (INVERT ? ~__ldg(bm + wi) : __ldg(bm + wi)) : 0u;
             if (wi == words - 1 && (T & 31)) bits &= (1u << (T & 31)) - 1u;     // padding bits of the last word
             const uint32_t cnt = __popc(bits);
             uint32_t incl = cnt;
@@ -97,6 +98,17 @@ __global__ void bitmap_expand_kernel(const uint64_t *__restrict__ col_ptr, const
             pos += __shfl_sync(FULL_MASK, incl, 31);
         }
     }
+}
+
+__global__ void bitmap_expand_kernel(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ bitmap, uint64_t n, uint64_t T,
+                                     uint32_t words, uint32_t *__restrict__ row_idx) {
+    bitmap_expand_body<false>(col_ptr, bitmap, n, T, words, row_idx);
+}
+// the CLEAR bits instead (the complement formulation's list of a series' missing time stamps, straight from the bitmap of its
+// observed ones: `col_ptr` then holds the offsets of the missing-cell lists)
+__global__ void bitmap_expand_inverted_kernel(const uint64_t *__restrict__ col_ptr, const uint32_t *__restrict__ bitmap, uint64_t n, uint64_t T,
+                                              uint32_t words, uint32_t *__restrict__ row_idx) {
+    bitmap_expand_body<true>(col_ptr, bitmap, n, T, words, row_idx);
 }
 
 // All arrays on the device; temporaries come from (and return to) the stream-ordered pool.  Returns a cudaError_t.

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -40,6 +41,10 @@
 // error plumbing
 // --------------------------------------------------------------------------
 static thread_local std::string g_last_error;
+// set by c_trmf_train around its trmf_b200_create: the caller's buffers outlive the session, so the host-side packing and the
+// enqueueing of the upload slabs may continue on a feeder thread after create has returned
+static thread_local bool g_async_feed = false;
+static thread_local bool g_on_feeder = false;     // this thread is a session's feeder: it waits politely, the caller needs a core
 
 static int fail(const char *fmt, ...) {
     char buf[1024];
@@ -79,6 +84,13 @@ struct trmf_b200_session {
     std::vector<size_t> slab_j;          // slab b = series [slab_j[b], slab_j[b+1])
     std::vector<cudaEvent_t> slab_ev;
     bool slabs_pending = false;          // the F-update has not consumed the slab events yet
+    // host-packed ingest inside c_trmf_train: a feeder thread packs + enqueues slab after slab while the calling thread already
+    // enqueues the first F-update; slab b may be waited for once slabs_published > b
+    std::thread feeder;
+    std::atomic<size_t> slabs_published{0};
+    std::atomic<int> feed_state{0};      // 0 = running / not used, 1 = finished, -1 = failed (feed_err)
+    size_t feed_plain_from = (size_t)-1; // slabs from this one on carry plain row indices (the bitmaps could not: unsorted input)
+    std::string feed_err;
     bool csr_deferred = false;           // the device transpose has not been issued yet
     uint32_t *pack_buf = nullptr;        // pinned staging of the host-packed index bitmap (back to the pool at destroy)
     uint32_t *bm_dev = nullptr;          // host-packed ingest: the bitmaps in HBM until the first consumer has expanded them
@@ -164,6 +176,10 @@ struct trmf_b200_session {
     double *cm_rhs = nullptr;         // max(T, n) x k: Y0^T W resp. Y0 H
     double *cm_cpart = nullptr;       // split-K scratch of the tall-skinny products
     size_t cm_cpart_elems = 0;
+    uint32_t *cm_bm0 = nullptr;       // while the lists are built: per series, bitmap of its missing time stamps ...
+    uint32_t *cm_bmT = nullptr;       // ... and per time stamp, bitmap of its missing series
+    size_t cm_placed = 0;             // the series [0, cm_placed) are in cm_idx[0], cm_Y0 and cm_bmT
+    bool cm_ready = false;            // by-time list and cm_yy are built
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
     size_t sys_batch = 0;             // series per batch
@@ -176,7 +192,9 @@ struct trmf_b200_session {
 
     // stats
     bool timing = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr, ev4 = nullptr, ev5 = nullptr, ev6 = nullptr, ev7 = nullptr, ev8 = nullptr;
+    bool cm_timed = false;
+    float ms_cmg = 0, ms_cmp = 0;        // complement F-update: Gram over the missing cells / tall-skinny product (last whole-Y pass)
     double st_cg = 0, st_acc = 0, st_f = 0, st_fnew = 0, st_gnorm = 0, st_prered = 0, st_actred = 0;
     double ms_f = 0, ms_x = 0, ms_lag = 0, ms_fk = 0, ms_xg = 0;
     unsigned long long launches = 0;
@@ -319,6 +337,36 @@ static void trace_pt(const char *what) {
     if (!strcmp(what, "begin")) t0 = t;
     fprintf(stderr, "[trmf-b200 trace] %8.3f ms  %s\n", t - t0, what);
 }
+// ... and the device side of the same call: timing events recorded on the streams at the points named below, printed (relative to the
+// first one) by trace_dev_dump() once the call has synchronised.  Nothing is recorded unless TRMF_B200_TRACE is set.
+static std::vector<std::pair<std::string, cudaEvent_t>> g_trace_ev;
+static std::mutex g_trace_mu;
+static void trace_dev(cudaStream_t st, const char *fmt, ...) {
+    static const bool on = getenv("TRMF_B200_TRACE") != nullptr;
+    if (!on) return;
+    char buf[160];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    cudaEvent_t ev;
+    if (cudaEventCreate(&ev) != cudaSuccess) return;
+    cudaEventRecord(ev, st);
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    g_trace_ev.emplace_back(buf, ev);
+}
+static void trace_dev_dump() {
+    std::lock_guard<std::mutex> lk(g_trace_mu);
+    if (g_trace_ev.empty()) return;
+    for (auto &pe : g_trace_ev) {
+        float ms = 0;
+        cudaEventSynchronize(pe.second);
+        cudaEventElapsedTime(&ms, g_trace_ev.front().second, pe.second);
+        fprintf(stderr, "[trmf-b200 trace] device %8.3f ms  %s\n", ms, pe.first.c_str());
+    }
+    for (auto &pe : g_trace_ev) cudaEventDestroy(pe.second);
+    g_trace_ev.clear();
+}
 // Branch-free packing at any density: one output word (32 rows) at a time.  The entries of word w are a prefix of what is left of
 // the (ascending) list, at most 32 of them: four 8-lane compares find and count them, a variable shift turns them into bits.
 // No data-dependent branch, so 10 % randomly missing rows cost nothing in mispredictions (a scan for the gaps between runs of
@@ -395,6 +443,9 @@ static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, 
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= (unsigned)std::max(1, atoi(e));   // one process per GPU: share the host cores
     if (const char *e = getenv("TRMF_B200_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
     nt = std::max(2u, std::min(nt, 32u));      // (nt - 1 packers + the calling thread)
+    // on a feeder thread the session's calling thread is busy enqueueing kernels at the same time: leave it a core
+    if (g_on_feeder && !getenv("TRMF_B200_PACK_THREADS") && nt > 4) nt -= 1;
+    const bool polite = g_on_feeder;
     bool avx2 = false;
 #if defined(__x86_64__)
     avx2 = __builtin_cpu_supports("avx2") && !getenv("TRMF_B200_PACK_SCALAR");
@@ -430,6 +481,7 @@ static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, 
     for (size_t b = 0; b < nsl && !*rc; ++b) {
         const size_t want = slab_j[b + 1] - slab_j[b];
         while (done[b].load(std::memory_order_acquire) < want && !bad.load(std::memory_order_relaxed)) {
+            if (polite) { std::this_thread::sleep_for(std::chrono::microseconds(10)); continue; }
 #if defined(__x86_64__)
             _mm_pause();
 #endif
@@ -516,6 +568,9 @@ static int session_common_init(S *s) {
     CUDA_TRY(cudaEventCreate(&s->ev3));
     CUDA_TRY(cudaEventCreate(&s->ev4));
     CUDA_TRY(cudaEventCreate(&s->ev5));
+    CUDA_TRY(cudaEventCreate(&s->ev6));
+    CUDA_TRY(cudaEventCreate(&s->ev7));
+    CUDA_TRY(cudaEventCreate(&s->ev8));
     return 0;
 }
 
@@ -535,12 +590,13 @@ extern "C" void trmf_b200_destroy(S *s) {
     cudaSetDevice(s->device);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->aux_stream) cudaStreamSynchronize(s->aux_stream);
+    if (s->feeder.joinable()) s->feeder.join();
     if (s->stream) cudaStreamSynchronize(s->stream);
     dist_teardown(s);
     dev_free(s->part_tk);
     dev_free(s->Gt); dev_free(s->bt); dev_free(s->Xs); dev_free(s->invs); dev_free(s->ysc); dev_free(s->frow); dev_free(s->sys); dev_free(s->valh); dev_free(s->bm_dev);
     dev_free(s->cm_ptr[0]); dev_free(s->cm_ptr[1]); dev_free(s->cm_idx[0]); dev_free(s->cm_idx[1]); dev_free(s->cm_Y0); dev_free(s->cm_yy);
-    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr);
+    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr); dev_free(s->cm_bm0); dev_free(s->cm_bmT);
     if (s->own_Y) {
         dev_free(s->row_ptr); dev_free(s->col_ptr); dev_free(s->col_idx); dev_free(s->row_idx);
         dev_free(s->val_t); dev_free(s->val); dev_free(s->Yd);
@@ -567,6 +623,9 @@ extern "C" void trmf_b200_destroy(S *s) {
     if (s->ev3) cudaEventDestroy(s->ev3);
     if (s->ev4) cudaEventDestroy(s->ev4);
     if (s->ev5) cudaEventDestroy(s->ev5);
+    if (s->ev6) cudaEventDestroy(s->ev6);
+    if (s->ev7) cudaEventDestroy(s->ev7);
+    if (s->ev8) cudaEventDestroy(s->ev8);
     if (s->stream) cudaStreamSynchronize(s->stream);   // the frees above are ordered on the stream
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -678,27 +737,44 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                 if (j > s->slab_j.back()) s->slab_j.push_back(j);
             }
             if (s->slab_j.back() < s->n) s->slab_j.push_back(s->n);
-            auto issue_slab = [&](size_t b) -> int {
-                const uint64_t e0 = Y->col_ptr[s->slab_j[b]], e1 = Y->col_ptr[s->slab_j[b + 1]];
+            const size_t nsl = s->slab_j.size() - 1;
+            // (everything below may run on the feeder thread after this function has returned: captures by value, events created here)
+            const uint64_t *h_col_ptr = Y->col_ptr;
+            const uint32_t *h_row_idx = Y->row_idx;
+            const V *h_val = (const V *)Y->val;
+            s->slab_ev.resize(nsl);
+            for (size_t b = 0; b < nsl; ++b) CUDA_TRY(cudaEventCreateWithFlags(&s->slab_ev[b], cudaEventDisableTiming));
+            auto issue_vals = [=](size_t b) -> int {
+                const uint64_t e0 = h_col_ptr[s->slab_j[b]], e1 = h_col_ptr[s->slab_j[b + 1]];
                 if (e1 > e0) {
-                    if (!idx_by_bitmap) CUDA_TRY(cudaMemcpyAsync(s->row_idx + e0, Y->row_idx + e0, (e1 - e0) * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
-                    CUDA_TRY(cudaMemcpyAsync(s->val + e0, (const V *)Y->val + e0, (e1 - e0) * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
+                    if (!idx_by_bitmap) CUDA_TRY(cudaMemcpyAsync(s->row_idx + e0, h_row_idx + e0, (e1 - e0) * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                    CUDA_TRY(cudaMemcpyAsync(s->val + e0, h_val + e0, (e1 - e0) * sizeof(V), cudaMemcpyHostToDevice, s->copy_stream));
                 }
-                cudaEvent_t ev;
-                CUDA_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                CUDA_TRY(cudaEventRecord(ev, s->copy_stream));
-                s->slab_ev.push_back(ev);
                 return 0;
             };
-            const size_t nsl = s->slab_j.size() - 1;
+            auto publish_slab = [=](size_t b) -> int {
+                CUDA_TRY(cudaEventRecord(s->slab_ev[b], s->copy_stream));
+                trace_dev(s->copy_stream, "copy stream: slab %zu landed", b);
+                s->slabs_published.store(b + 1, std::memory_order_release);
+                return 0;
+            };
             trace_pt("create: allocations done, issuing slabs");
+            trace_dev(s->copy_stream, "copy stream: first copy issued (host mark 'issuing slabs')");
+            s->slabs_published.store(0);
+            s->feed_state.store(0);
             if (!host_pack) {
-                for (size_t b = 0; b < nsl; ++b) if (issue_slab(b)) return 1;
+                for (size_t b = 0; b < nsl; ++b) if (issue_vals(b) || publish_slab(b)) return 1;
+                s->feed_state.store(1);
             } else {
                 // host-packed indices, slab by slab: the host cores pack the bitmaps of slab b while the copy engine is busy with
-                // slab b-1; each slab's bitmap goes out right in front of its values, and the F-update of slab b expands the bitmap
-                // on the device as soon as both have landed (trmf_b200_f_update / wait_slabs).  (Round-2 history: all bitmaps
-                // packed first = the F-update started 6 ms into the call and the copy engine idled for 1 ms: 17.5 ms end to end.)
+                // the VALUES of slab b (which need no packing and go out one slab ahead: the copy engine starts at once and never
+                // waits for a packer); each slab's bitmap follows its values, and the F-update of slab b expands the bitmap on
+                // the device as soon as both have landed (trmf_b200_f_update / slab_wait).  Inside c_trmf_train all of this runs
+                // on a FEEDER THREAD, so that the calling thread can enqueue the first F-update's per-slab kernels while the
+                // slabs are still being packed -- otherwise the compute stream stays empty until the last slab is packed and
+                // the slab-wise F-update runs behind the upload instead of under it (measured: 5 ms of an 13 ms call).
+                // (Round-2 history: all bitmaps packed first = 17.5 ms end to end at C2; bitmap in front of its values = the
+                // copy engine idled through the first slab's packing; F-update enqueued after the packing = 13.2 ms.)
                 const size_t bytes = (size_t)s->n * bm_words * sizeof(uint32_t);
                 s->pack_buf = bitmap_buf_get(bytes, &s->pack_bytes);
                 if (!s->pack_buf) return fail("cannot allocate %zu bytes of pinned memory for the index bitmaps", bytes);
@@ -706,24 +782,46 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
                 s->bm_words = bm_words;
                 CUDA_TRY(cudaEventRecord(s->csr_ready, s->stream));             // (bm_dev's allocation is ordered on s->stream)
                 CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, s->csr_ready, 0));
-                int rc = 0;
-                auto slab_packed = [&](size_t b) -> int {
-                    const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
-                    CUDA_TRY(cudaMemcpyAsync(s->bm_dev + j0 * (size_t)bm_words, s->pack_buf + j0 * (size_t)bm_words,
-                                             (j1 - j0) * (size_t)bm_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
-                    return issue_slab(b);
+                const uint64_t rowsT = s->T, nnz_all = s->nnz;
+                auto feed = [=]() -> int {
+                    if (cudaSetDevice(s->device) != cudaSuccess) return fail("feeder: cudaSetDevice failed");
+                    int rc = 0;
+                    auto slab_packed = [=](size_t b) -> int {
+                        const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
+                        CUDA_TRY(cudaMemcpyAsync(s->bm_dev + j0 * (size_t)bm_words, s->pack_buf + j0 * (size_t)bm_words,
+                                                 (j1 - j0) * (size_t)bm_words * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                        if (publish_slab(b)) return 1;
+                        return b + 1 < nsl ? issue_vals(b + 1) : 0;
+                    };
+                    if (issue_vals(0)) return 1;
+                    const bool packed = pack_bitmap_slabs(h_col_ptr, h_row_idx, s->slab_j, bm_words, rowsT, s->pack_buf, slab_packed, &rc);
+                    trace_pt("feeder: host pack done, every slab enqueued");
+                    if (rc) return 1;
+                    if (!packed) {
+                        // unsorted or duplicate indices from some slab on: the whole row_idx array goes over as it is, then the
+                        // values of the slabs that are still missing; their events are recorded behind it, so nothing reads those
+                        // indices before they are complete (the slabs published so far were carried by their bitmaps -- same
+                        // indices -- and may already have been consumed)
+                        const size_t done = s->slabs_published.load();
+                        s->feed_plain_from = done;
+                        CUDA_TRY(cudaMemcpyAsync(s->row_idx, h_row_idx, nnz_all * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
+                        for (size_t b = done; b < nsl; ++b) if (issue_vals(b) || publish_slab(b)) return 1;
+                    }
+                    return 0;
                 };
-                const bool packed = pack_bitmap_slabs(Y->col_ptr, Y->row_idx, s->slab_j, bm_words, s->T, s->pack_buf, slab_packed, &rc);
-                trace_pt("create: host pack done, every slab enqueued");
-                if (rc) return 1;
-                if (!packed) {
-                    // unsorted or duplicate indices: the whole row_idx array goes over as it is, then whatever slabs are still
-                    // missing; every slab event is (re-)recorded behind it, so nothing reads row_idx before it is complete
-                    dev_free(s->bm_dev);
-                    s->bm_dev = nullptr;
-                    CUDA_TRY(cudaMemcpyAsync(s->row_idx, Y->row_idx, s->nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, s->copy_stream));
-                    for (size_t b = s->slab_ev.size(); b < nsl; ++b) if (issue_slab(b)) return 1;
-                    for (cudaEvent_t ev : s->slab_ev) CUDA_TRY(cudaEventRecord(ev, s->copy_stream));
+                const bool async = g_async_feed;
+                auto feed_main = [=]() {
+                    g_on_feeder = async;
+                    const int rc = feed();
+                    g_on_feeder = false;
+                    if (rc) s->feed_err = g_last_error.empty() ? std::string("feeder thread failed") : g_last_error;
+                    s->feed_state.store(rc ? -1 : 1, std::memory_order_release);
+                };
+                if (g_async_feed) {
+                    s->feeder = std::thread(feed_main);
+                } else {
+                    feed_main();      // (a caller of trmf_b200_create may release its buffers when the call returns)
+                    if (s->feed_state.load() < 0) return fail("%s", s->feed_err.c_str());
                 }
             }
             s->slabs_pending = true;
@@ -906,14 +1004,30 @@ extern "C" int trmf_b200_sync(S *s) {
 // host-packed ingest: row indices of the series [j0, j1) out of their bitmaps (the slab's copies are already waited for)
 static int expand_slab_bitmaps(S *s, size_t j0, size_t j1) {
     if (!s->bm_dev || j1 <= j0) return 0;
+    if (s->feed_plain_from != (size_t)-1) {      // the feeder fell back to plain indices from that slab on
+        const size_t jp = s->slab_j[std::min(s->feed_plain_from, s->slab_j.size() - 1)];
+        if (j0 >= jp) return 0;
+        j1 = std::min(j1, jp);
+    }
     const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>((size_t)s->num_sms * 8, (j1 - j0 + 7) / 8));
     bitmap_expand_kernel<<<grid, 256, 0, s->stream>>>(s->col_ptr + j0, s->bm_dev + j0 * (size_t)s->bm_words, j1 - j0, s->T, s->bm_words, s->row_idx);
     s->launches++;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
+// slab b of a slab-wise upload is on its way: make the session stream wait for it (a feeder thread may still be packing it)
+static int slab_wait(S *s, size_t b) {
+    while (s->slabs_published.load(std::memory_order_acquire) <= b) {
+        if (s->feed_state.load(std::memory_order_acquire) < 0) return fail("%s", s->feed_err.c_str());
+        std::this_thread::sleep_for(std::chrono::microseconds(20));
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
+    return 0;
+}
 static int wait_slabs(S *s) {
     if (!s->slabs_pending) return 0;
+    if (s->feeder.joinable()) s->feeder.join();
+    if (s->feed_state.load() < 0) return fail("%s", s->feed_err.c_str());
     for (cudaEvent_t e : s->slab_ev) CUDA_TRY(cudaStreamWaitEvent(s->stream, e, 0));
     if (s->bm_dev) {
         if (expand_slab_bitmaps(s, 0, s->n)) return 1;
@@ -1248,40 +1362,31 @@ static bool cm_on(S *s) {
     s->cm_state = 1;
     return true;
 }
-// index list of the missing cells of every row of one orientation (o = 0: by series from the CSC half, 1: by time from the CSR half)
-static int cm_build_index(S *s, int o) {
-    if (s->cm_ptr[o]) return 0;
-    const uint64_t rows = o == 0 ? s->n : s->T, dim = o == 0 ? s->T : s->n;
-    const uint64_t *ptr = o == 0 ? s->col_ptr : s->row_ptr;
-    const uint32_t *idx = o == 0 ? s->row_idx : s->col_idx;
-    const uint64_t nmiss = rows * dim - s->nnz;
-    const uint32_t words = (uint32_t)((dim + 31) / 32);
-    uint64_t *cnt = nullptr;
-    uint32_t *bm = nullptr;
+// Everything the formulation derives from Y comes out of the by-series CSC alone, series range by series range, so that a
+// host-buffer session can place each slab while the next one is still crossing PCIe and never needs the by-time CSR:
+//   cm_begin   allocations, cm_ptr[0] (a scan over T - the series' lengths: needs col_ptr only), zeroed Y0 and bitmaps
+//   cm_place   one range of series: its missing time stamps (cm_idx[0]), its column block of Y0, its bits of the per-time-stamp bitmaps
+//   cm_finish  per time stamp: the missing series (cm_ptr[1] / cm_idx[1], ascending) out of the bitmaps, sum of squares of Y0's row
+static int cm_scan(S *s, const uint64_t *cnt, uint64_t *out, uint64_t items) {
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    if (dev_alloc(&s->cm_ptr[o], rows + 1) || dev_alloc(&s->cm_idx[o], std::max<uint64_t>(nmiss, 1)) || dev_alloc(&cnt, rows + 1) ||
-        dev_alloc(&bm, rows * (size_t)words))
-        return 1;
-    const unsigned grid = (unsigned)(s->num_sms * 8);
-    LAUNCH(s, cm::count_missing_kernel, (unsigned)std::min<uint64_t>((rows + 256) / 256, grid), 256, 0, ptr, rows, dim, cnt);
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, s->cm_ptr[o], (int64_t)(rows + 1), s->stream));
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, cnt, out, (int64_t)items, s->stream));
     CUDA_TRY(cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 1, s->stream));
-    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, s->cm_ptr[o], (int64_t)(rows + 1), s->stream));
-    LAUNCH(s, cm::missing_bitmap_kernel, grid, 256, 0, ptr, idx, rows, words, bm);
-    LAUNCH(s, bitmap_expand_kernel, grid, 256, 0, s->cm_ptr[o], bm, rows, dim, words, s->cm_idx[o]);
+    CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, cnt, out, (int64_t)items, s->stream));
     s->launches++;
     CUDA_TRY(cudaFreeAsync(tmp, s->stream));
-    dev_free(cnt);
-    dev_free(bm);
     return 0;
 }
-// everything that depends on Y only: both index lists, the zero-filled dense copy, the rows' sums of squares, scratch
-static int cm_build(S *s) {
+static int cm_begin(S *s) {
     if (s->cm_Y0) return 0;
-    if (need_csr(s)) return 1;
-    if (cm_build_index(s, 0) || cm_build_index(s, 1)) return 1;
     const size_t rmax = std::max(Tcap(s), s->n), k = (size_t)s->k;
+    const uint64_t nmiss = s->T * s->n - s->nnz;
+    const uint32_t w0 = (uint32_t)((s->T + 31) / 32), wT = (uint32_t)((s->n + 31) / 32);
+    uint64_t *cnt = nullptr;
+    if (dev_alloc(&s->cm_ptr[0], s->n + 1) || dev_alloc(&s->cm_idx[0], std::max<uint64_t>(nmiss, 1)) || dev_alloc(&s->cm_ptr[1], s->T + 1) ||
+        dev_alloc(&s->cm_idx[1], std::max<uint64_t>(nmiss, 1)) || dev_alloc(&cnt, s->n + 1) || dev_alloc(&s->cm_bm0, s->n * (size_t)w0) ||
+        dev_alloc(&s->cm_bmT, s->T * (size_t)wT))
+        return 1;
     if (dev_alloc(&s->cm_Y0, s->T * s->n) || dev_alloc(&s->cm_yy, s->T) || dev_alloc(&s->cm_FtF, k * k) || dev_alloc(&s->cm_rhs, rmax * k) ||
         dev_alloc(&s->cm_Xr, rmax * k))
         return 1;
@@ -1291,45 +1396,92 @@ static int cm_build(S *s) {
         s->Cpart_elems = k * k * 512;
         if (dev_alloc(&s->Cpart, s->Cpart_elems)) return 1;
     }
-    CUDA_TRY(cudaMemsetAsync(s->cm_Y0, 0, s->T * s->n * sizeof(float), s->stream));
     const unsigned grid = (unsigned)(s->num_sms * 8);
-    LAUNCH(s, cm::scatter_dense_kernel, grid, 256, 0, s->row_ptr, s->col_idx, s->val_t, (uint64_t)s->T, (uint64_t)s->n, s->cm_Y0);
-    LAUNCH(s, cm::row_sumsq_kernel, grid, 256, 0, s->row_ptr, s->val_t, (uint64_t)s->T, s->cm_yy);
+    LAUNCH(s, cm::count_missing_kernel, (unsigned)std::min<uint64_t>((s->n + 256) / 256, grid), 256, 0, s->col_ptr, s->n, s->T, cnt);
+    if (cm_scan(s, cnt, s->cm_ptr[0], s->n + 1)) return 1;
+    dev_free(cnt);
+    CUDA_TRY(cudaMemsetAsync(s->cm_Y0, 0, s->T * s->n * sizeof(float), s->stream));
+    CUDA_TRY(cudaMemsetAsync(s->cm_bmT, 0, s->T * (size_t)wT * sizeof(uint32_t), s->stream));
+    s->cm_placed = 0;
+    s->cm_ready = false;
     return 0;
 }
+static int cm_place(S *s, size_t j0, size_t j1) {
+    if (j1 <= j0) return 0;
+    if (j0 != s->cm_placed) return fail("internal: complement ranges out of order (%zu after %zu)", j0, s->cm_placed);
+    const uint64_t rows = j1 - j0;
+    const uint32_t w0 = (uint32_t)((s->T + 31) / 32), wT = (uint32_t)((s->n + 31) / 32);
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)s->num_sms * 8, (rows + 7) / 8));
+    const bool have_bm = s->bm_dev && s->bm_words == w0 &&
+                         (s->feed_plain_from == (size_t)-1 || j1 <= s->slab_j[std::min(s->feed_plain_from, s->slab_j.size() - 1)]);
+    if (have_bm) {
+        // host-packed ingest: the bitmap of the series' OBSERVED time stamps is still in HBM -- its clear bits are the list
+        LAUNCH(s, bitmap_expand_inverted_kernel, grid, 256, 0, s->cm_ptr[0] + j0, s->bm_dev + j0 * (size_t)w0, rows, s->T, w0, s->cm_idx[0]);
+    } else {
+        uint32_t *bm = s->cm_bm0 + j0 * (size_t)w0;
+        LAUNCH(s, cm::missing_bitmap_kernel, grid, 256, 0, s->col_ptr + j0, s->row_idx, rows, w0, bm);
+        LAUNCH(s, bitmap_expand_kernel, grid, 256, 0, s->cm_ptr[0] + j0, bm, rows, s->T, w0, s->cm_idx[0]);
+    }
+    LAUNCH(s, cm::scatter_dense_csc_kernel, dim3((unsigned)((rows + 31) / 32), cm::SC_CHUNKS / 8), dim3(32, 8), 0, s->col_ptr + j0, s->row_idx,
+           s->val, rows, (uint64_t)s->n, s->cm_Y0 + j0);
+    LAUNCH(s, cm::transpose_missing_kernel, grid, 256, 0, s->cm_ptr[0] + j0, s->cm_idx[0], rows, (uint64_t)j0, wT, s->cm_bmT);
+    s->cm_placed = j1;
+    return 0;
+}
+static int cm_finish(S *s) {
+    if (s->cm_ready) return 0;
+    if (s->cm_placed != s->n) return fail("internal: complement finished with %zu of %zu series placed", s->cm_placed, (size_t)s->n);
+    const uint32_t wT = (uint32_t)((s->n + 31) / 32);
+    const unsigned grid = (unsigned)(s->num_sms * 8);
+    uint64_t *cnt = nullptr;
+    if (dev_alloc(&cnt, s->T + 1)) return 1;
+    LAUNCH(s, cm::count_bits_kernel, grid, 256, 0, s->cm_bmT, (uint64_t)s->T, (uint64_t)s->n, wT, cnt);
+    if (cm_scan(s, cnt, s->cm_ptr[1], s->T + 1)) return 1;
+    LAUNCH(s, bitmap_expand_kernel, grid, 256, 0, s->cm_ptr[1], s->cm_bmT, (uint64_t)s->T, (uint64_t)s->n, wT, s->cm_idx[1]);
+    LAUNCH(s, cm::row_sumsq_dense_kernel, grid, 256, 0, s->cm_Y0, (uint64_t)s->T, (uint64_t)s->n, s->cm_yy);
+    dev_free(cnt);
+    dev_free(s->cm_bm0); s->cm_bm0 = nullptr;
+    dev_free(s->cm_bmT); s->cm_bmT = nullptr;
+    s->cm_ready = true;
+    return 0;
+}
+// the whole of it at once (Y resident, or whatever a slab-wise F-update has not placed yet)
+static int cm_build(S *s) {
+    if (s->cm_ready) return 0;
+    if (cm_begin(s)) return 1;
+    if (s->cm_placed < s->n && (wait_slabs(s) || cm_place(s, s->cm_placed, s->n))) return 1;
+    return cm_finish(s);
+}
 template <int NB>
-static int cm_gemm_t(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
+static int cm_gemm_t(S *s, const float *A, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
     const int N = s->k;
     auto kfn = cm::gemm64_partial_kernel<NB>;
     const size_t smem = cm::gemm64_smem<NB>();
     CUDA_TRY(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 128, smem));
-    const size_t slots = (size_t)s->num_sms * (size_t)std::max(per_sm, 1), mt = (M + cm::GM - 1) / cm::GM;
-    // whole waves: mt x splits CTAs should not spill a few stragglers into another round of the resident CTAs
-    size_t splits = std::max<size_t>(1, slots / mt);
-    splits = std::min(splits, std::max<size_t>(1, K / 256));
-    splits = std::min(splits, std::max<size_t>(1, s->cm_cpart_elems / (M * (size_t)N)));
-    size_t kchunk = (K + splits - 1) / splits;
+    // split-K by K alone (up to 16 parts of at least 256): a row's sums then do not depend on how many rows the call covers, and
+    // a series slab of a host-buffer session gets the same right-hand sides as the whole Y at once
+    const size_t mt = (M + cm::GM - 1) / cm::GM;
+    size_t kchunk = std::max<size_t>(256, (K + 15) / 16);
     kchunk = (kchunk + cm::GK - 1) / cm::GK * cm::GK;
-    splits = (K + kchunk - 1) / kchunk;
+    const size_t splits = (K + kchunk - 1) / kchunk;
+    if (M * (size_t)N * splits > s->cm_cpart_elems) return fail("internal: split-K scratch too small (%zu rows)", M);
     dim3 grid((unsigned)mt, (unsigned)splits);
-    LAUNCH(s, kfn, grid, 128, smem, s->cm_Y0, sm, sk, B, M, N, K, kchunk, s->cm_cpart);
+    LAUNCH(s, kfn, grid, 128, smem, A, sm, sk, B, M, N, K, kchunk, s->cm_cpart);
     LAUNCH(s, (gemm_finish_kernel<double>), ew_grid(s, M * (size_t)N), 256, 0, s->cm_cpart, (int)splits, M * (size_t)N, N, 1.0,
            (const V *)nullptr, 0.0, 0.0, out, (const int *)nullptr);
     return 0;
 }
-// out (M x k, fp64) = A B with A(m, kappa) = Y0[m * sm + kappa * sk]
-static int cm_gemm(S *s, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
+// out (M x k, fp64) = A B with A(m, kappa) = A[m * sm + kappa * sk] (a block of Y0)
+static int cm_gemm(S *s, const float *A, size_t sm, size_t sk, const V *B, size_t M, size_t K, double *out) {
     switch ((s->k + 7) / 8) {      // 8-column accumulator blocks
-        case 1: return cm_gemm_t<1>(s, sm, sk, B, M, K, out);
-        case 2: return cm_gemm_t<2>(s, sm, sk, B, M, K, out);
-        case 3: return cm_gemm_t<3>(s, sm, sk, B, M, K, out);
-        case 4: return cm_gemm_t<4>(s, sm, sk, B, M, K, out);
-        case 5: return cm_gemm_t<5>(s, sm, sk, B, M, K, out);
-        case 6: return cm_gemm_t<6>(s, sm, sk, B, M, K, out);
-        case 7: return cm_gemm_t<7>(s, sm, sk, B, M, K, out);
-        default: return cm_gemm_t<8>(s, sm, sk, B, M, K, out);
+        case 1: return cm_gemm_t<1>(s, A, sm, sk, B, M, K, out);
+        case 2: return cm_gemm_t<2>(s, A, sm, sk, B, M, K, out);
+        case 3: return cm_gemm_t<3>(s, A, sm, sk, B, M, K, out);
+        case 4: return cm_gemm_t<4>(s, A, sm, sk, B, M, K, out);
+        case 5: return cm_gemm_t<5>(s, A, sm, sk, B, M, K, out);
+        case 6: return cm_gemm_t<6>(s, A, sm, sk, B, M, K, out);
+        case 7: return cm_gemm_t<7>(s, A, sm, sk, B, M, K, out);
+        default: return cm_gemm_t<8>(s, A, sm, sk, B, M, K, out);
     }
 }
 static int ensure_sys(S *s) {
@@ -1338,40 +1490,87 @@ static int ensure_sys(S *s) {
     s->sys_batch = std::max<size_t>(1, std::min<size_t>(std::max(s->n, Tcap(s)), ((size_t)1 << 30) / (sysd * sizeof(double))));
     return dev_alloc(&s->sys, s->sys_batch * sysd);
 }
-// F-update of every series through the complement
-static int cm_f_update(S *s) {
+// F-update of the series [j0, j1) through the complement (their range is placed: cm_place); `first` = first range of this F-update:
+// W is split into fp16 pairs and its k x k Gram summed once
+static int cm_f_range(S *s, size_t j0, size_t j1, bool first) {
     const int k = s->k;
-    if (cm_build(s) || ensure_sys(s)) return 1;
+    if (ensure_sys(s)) return 1;
     const size_t smem = sizeof(double) * ((size_t)(k + 1) * (k + 1) + k);
-    for (size_t b0 = 0; b0 < s->n; b0 += s->sys_batch) {
-        const size_t b1 = std::min(s->n, b0 + s->sys_batch);
+    // threads per system of the deferred solve: 64 / 128 = one CTA per system, 32 = one warp per system on packed triangular storage.
+    // Measured at C2 (10 000 systems of 40): 0.949 / 0.955 / 0.992 ms per F-update for 64 / 32 / 128 -- identical factors.
+    int solve_nt = 64;
+    if (const char *e = getenv("TRMF_B200_SOLVE_THREADS")) solve_nt = atoi(e);
+    for (size_t b0 = j0; b0 < j1; b0 += s->sys_batch) {
+        const size_t b1 = std::min(j1, b0 + s->sys_batch);
+        const bool head = first && b0 == j0;
+        const bool timed = s->timing && b0 == 0 && b1 == s->n;
+        if (timed) CUDA_TRY(cudaEventRecord(s->ev6, s->stream));
         // (the first launch splits W into fp16 pairs and leaves the values the split carries in cm_Xr: the products below read those)
         if (f_update_mma2_launch<fm::MODE_GONLY>(s->stream, s->num_sms, s->cm_ptr[0] + b0, s->cm_idx[0], (const V *)nullptr, s->W, s->T, s->Xs,
                                                  s->invs, (V *)nullptr, (V *)nullptr, k, 0.0, (uint32_t)(b1 - b0), s->queue, &s->launches,
-                                                 nullptr, 0, s->sys, b0 == 0, nullptr, s->cm_Xr))
+                                                 nullptr, 0, s->sys, head, nullptr, s->cm_Xr, (uint32_t)std::min<size_t>(s->n, s->sys_batch)))
             return fail("complement Gram launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        if (b0 == 0) {
-            if (gemm<V, V, double>(s, s->cm_Xr, 1, (size_t)k, s->cm_Xr, (size_t)k, k, s->T, 1.0, nullptr, 0.0, 0.0, s->cm_FtF)) return 1;
-            if (cm_gemm(s, 1, s->n, s->cm_Xr, s->n, s->T, s->cm_rhs)) return 1;
-        }
+        if (timed) CUDA_TRY(cudaEventRecord(s->ev7, s->stream));
+        if (b0 == j0 && cm_gemm(s, s->cm_Y0 + j0, 1, s->n, s->cm_Xr, j1 - j0, s->T, s->cm_rhs + j0 * (size_t)k)) return 1;
+        if (timed) CUDA_TRY(cudaEventRecord(s->ev8, s->stream));
+        s->cm_timed = timed;
+        if (head && gemm<V, V, double>(s, s->cm_Xr, 1, (size_t)k, s->cm_Xr, (size_t)k, k, s->T, 1.0, nullptr, 0.0, 0.0, s->cm_FtF)) return 1;
         unsigned grid = 1;
-#define CM_SOLVE(KK)                                                                                                         \
-    case KK: {                                                                                                               \
-        CUDA_TRY(cudaFuncSetAttribute(cm::solve_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));         \
+#define CM_SOLVE_NT(KK, NT)                                                                                                  \
+    do {                                                                                                                     \
+        CUDA_TRY(cudaFuncSetAttribute(cm::solve_kernel<KK, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));     \
         int per_sm = 0;                                                                                                      \
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cm::solve_kernel<KK>, 128, smem));                    \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cm::solve_kernel<KK, NT>, NT, smem));                 \
         grid = (unsigned)std::max<size_t>(1, std::min<size_t>(b1 - b0, (size_t)s->num_sms * (size_t)std::max(per_sm, 1)));    \
-        LAUNCH(s, cm::solve_kernel<KK>, grid, 128, smem, s->col_ptr + b0, s->cm_ptr[0] + b0, s->sys, s->cm_FtF, s->cm_rhs + b0 * (size_t)k, \
-               s->H + b0 * (size_t)k, s->lambdaI, (uint32_t)(b1 - b0));                                                      \
-        break;                                                                                                               \
-    }
+        LAUNCH(s, (cm::solve_kernel<KK, NT>), grid, NT, smem, s->col_ptr + b0, s->cm_ptr[0] + b0, s->sys, s->cm_FtF,          \
+               s->cm_rhs + b0 * (size_t)k, s->H + b0 * (size_t)k, s->lambdaI, (uint32_t)(b1 - b0));                          \
+    } while (0)
+#define CM_SOLVE_WARP(KK)                                                                                                    \
+    do {                                                                                                                     \
+        const size_t smw = cm::solve_warp_smem<KK>();                                                                        \
+        CUDA_TRY(cudaFuncSetAttribute(cm::solve_warp_kernel<KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smw));     \
+        int per_sm = 0;                                                                                                      \
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cm::solve_warp_kernel<KK>, 32, smw));                 \
+        grid = (unsigned)std::max<size_t>(1, std::min<size_t>(b1 - b0, (size_t)s->num_sms * (size_t)std::max(per_sm, 1)));    \
+        LAUNCH(s, (cm::solve_warp_kernel<KK>), grid, 32, smw, s->col_ptr + b0, s->cm_ptr[0] + b0, s->sys, s->cm_FtF,          \
+               s->cm_rhs + b0 * (size_t)k, s->H + b0 * (size_t)k, s->lambdaI, (uint32_t)(b1 - b0));                          \
+    } while (0)
+#define CM_SOLVE(KK)                                                                                                         \
+    case KK:                                                                                                                 \
+        if (solve_nt == 32) CM_SOLVE_WARP(KK); else if (solve_nt == 64) CM_SOLVE_NT(KK, 64); else CM_SOLVE_NT(KK, 128);      \
+        break;
         switch (k) {
             CM_SOLVE(8) CM_SOLVE(12) CM_SOLVE(16) CM_SOLVE(20) CM_SOLVE(24) CM_SOLVE(28) CM_SOLVE(32) CM_SOLVE(36) CM_SOLVE(40) CM_SOLVE(44)
             CM_SOLVE(48) CM_SOLVE(52) CM_SOLVE(56) CM_SOLVE(60) CM_SOLVE(64)
             default: return fail("internal: complement solve for k = %d", k);
         }
+#undef CM_SOLVE_NT
+#undef CM_SOLVE_WARP
 #undef CM_SOLVE
     }
+    return 0;
+}
+// F-update of every series.  A host-buffer session whose series slabs are still on their way places and solves slab after slab,
+// each as soon as it has landed (the by-time CSR is not needed, hence never built for a call that stays on this path).
+static int cm_f_update(S *s) {
+    if (s->cm_ready || !s->slabs_pending) return cm_build(s) || cm_f_range(s, 0, s->n, true);
+    if (cm_begin(s)) return 1;
+    trace_pt("F-update: complement scratch enqueued");
+    for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
+        const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
+        if (slab_wait(s, b)) return 1;
+        if (b < 2) trace_pt("F-update: slab published, enqueueing its kernels");
+        if (expand_slab_bitmaps(s, j0, j1)) return 1;
+        if (b == 0) trace_dev(s->stream, "F-update: slab 0 expanded (scratch zeroed before it)");
+        if (j1 > s->cm_placed && cm_place(s, j0, j1)) return 1;
+        if (b == 0) trace_dev(s->stream, "F-update: slab 0 placed");
+        if (cm_f_range(s, j0, j1, b == 0)) return 1;
+        trace_dev(s->stream, "F-update: slab %zu placed and solved", b);
+    }
+    if (s->bm_dev) { dev_free(s->bm_dev); s->bm_dev = nullptr; }
+    s->slabs_pending = false;
+    if (cm_finish(s)) return 1;
+    trace_dev(s->stream, "F-update: complement lists by time stamp finished");
     return 0;
 }
 // X-update: per-time-stamp Grams (fp32, s->Gt) + loss gradient into gout (added when gaccum) + sum of squared residuals per row
@@ -1386,12 +1585,12 @@ static int cm_x_gram(S *s, V *gout, int gaccum) {
             return fail("complement Gram launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         if (b0 == 0) {
             if (gemm<V, V, double>(s, s->cm_Xr, 1, (size_t)k, s->cm_Xr, (size_t)k, k, s->n, 1.0, nullptr, 0.0, 0.0, s->cm_FtF)) return 1;
-            if (cm_gemm(s, s->n, 1, s->cm_Xr, s->T, s->n, s->cm_rhs)) return 1;
+            if (cm_gemm(s, s->cm_Y0, s->n, 1, s->cm_Xr, s->T, s->n, s->cm_rhs)) return 1;
         }
         const unsigned grid = (unsigned)std::max<size_t>(1, std::min<size_t>(b1 - b0, (size_t)s->num_sms * 8));
 #define CM_XGRAM(KK)                                                                                                         \
     case KK:                                                                                                                 \
-        LAUNCH(s, cm::xgram_kernel<KK>, grid, 128, 0, s->row_ptr + b0, s->cm_ptr[1] + b0, s->sys, s->cm_FtF, s->cm_rhs + b0 * (size_t)k, \
+        LAUNCH(s, cm::xgram_kernel<KK>, grid, 128, 0, (uint64_t)s->n, s->cm_ptr[1] + b0, s->sys, s->cm_FtF, s->cm_rhs + b0 * (size_t)k, \
                s->cm_yy + b0, s->W + b0 * (size_t)k, gout + b0 * (size_t)k, s->Gt + b0 * (size_t)k * k, gaccum, s->frow + b0,  \
                (uint32_t)(b1 - b0));                                                                                         \
         break;
@@ -1407,7 +1606,8 @@ static int cm_x_gram(S *s, V *gout, int gaccum) {
 // Y changed (a rolling session moved its window): everything derived from it goes, the decision is taken again
 static void cm_reset(S *s) {
     dev_free(s->cm_ptr[0]); dev_free(s->cm_ptr[1]); dev_free(s->cm_idx[0]); dev_free(s->cm_idx[1]); dev_free(s->cm_Y0); dev_free(s->cm_yy);
-    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr);
+    dev_free(s->cm_FtF); dev_free(s->cm_rhs); dev_free(s->cm_cpart); dev_free(s->cm_Xr); dev_free(s->cm_bm0); dev_free(s->cm_bmT);
+    s->cm_bm0 = s->cm_bmT = nullptr; s->cm_placed = 0; s->cm_ready = false;
     s->cm_ptr[0] = s->cm_ptr[1] = nullptr; s->cm_idx[0] = s->cm_idx[1] = nullptr;
     s->cm_Y0 = nullptr; s->cm_yy = nullptr; s->cm_FtF = nullptr; s->cm_rhs = nullptr; s->cm_cpart = nullptr; s->cm_Xr = nullptr;
     s->cm_cpart_elems = 0;
@@ -1497,12 +1697,12 @@ extern "C" int trmf_b200_f_update(S *s) {
         if (fk == F_KERNEL_MMA) {
             if (mma_scratch(s)) return 1;
             if (cm_on(s)) {
-                // mostly observed Y: the complement formulation (needs the whole of Y: a slab-wise upload is waited for)
-                if (wait_slabs(s) || cm_f_update(s)) return 1;
+                // mostly observed Y: the complement formulation (slab by slab while a host-buffer session's upload is under way)
+                if (cm_f_update(s)) return 1;
             } else if (s->slabs_pending) {
                 // first F-update of a host-buffer session: one launch per series slab, each as soon as its slab has landed
                 for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
-                    CUDA_TRY(cudaStreamWaitEvent(s->stream, s->slab_ev[b], 0));
+                    if (slab_wait(s, b)) return 1;
                     if (expand_slab_bitmaps(s, s->slab_j[b], s->slab_j[b + 1])) return 1;
                     if (mma_f_range(s, s->slab_j[b], s->slab_j[b + 1], b == 0)) return 1;
                 }
@@ -1553,6 +1753,11 @@ extern "C" int trmf_b200_f_update(S *s) {
         CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         s->ms_f = ms;
         if (s->missing) { CUDA_TRY(cudaEventElapsedTime(&ms, s->ev2, s->ev3)); s->ms_fk = ms; }
+        if (s->cm_timed) {
+            CUDA_TRY(cudaEventElapsedTime(&ms, s->ev6, s->ev7)); s->ms_cmg = ms;
+            CUDA_TRY(cudaEventElapsedTime(&ms, s->ev7, s->ev8)); s->ms_cmp = ms;
+            s->cm_timed = false;
+        }
     }
     return 0;
 }
@@ -1565,7 +1770,16 @@ extern "C" int trmf_b200_x_update(S *s) {
     g_last_error.clear();
     CUDA_TRY(cudaSetDevice(s->device));
     if (s->timing) CUDA_TRY(cudaEventRecord(s->ev0, s->stream));
-    if (need_csr(s)) return 1;
+    // The by-time CSR serves the walks over Omega.  The complement formulation with per-time-stamp Grams (Gram build, gradient,
+    // objective, Hessian products and f(w + s) all come from the Grams) never touches it: a host-buffer session on that path does
+    // not even build it.
+    bool csr_free = s->missing && cm_on(s) && !getenv("TRMF_B200_NO_FUSED_GRAD") && !getenv("TRMF_B200_WALK_FNEW") &&
+                    !getenv("TRMF_B200_NO_GRAM_HV");
+    if (csr_free) {
+        if (gram_prepare(s)) return 1;
+        csr_free = s->gram_state == 1;
+    }
+    if (!csr_free && need_csr(s)) return 1;
     const size_t tk = s->T * (size_t)s->k;
     const unsigned eg = ew_grid(s, tk);
     const double eps_cg = 0.1, eta0 = 1e-4, eta1 = 0.25, eta2 = 0.75, sigma1 = 0.25, sigma2 = 0.5, sigma3 = 4.0;
@@ -1806,6 +2020,7 @@ extern "C" int trmf_b200_train(S *s, int32_t max_iter, int32_t period_W, int32_t
         if (iter % period_W == 0) {
             if (trmf_b200_x_update(s)) return 1;
             trace_pt("train: X-update returned (its scalars were read back)");
+            trace_dev(s->stream, "X-update done");
             if (verbose >= 2) {
                 fprintf(stdout, "iter %2d act %5.3e pre %5.3e delta %5.3e f %5.3e |g| %5.3e CG %3d |g| %5.3e\n", 1, s->st_actred,
                         s->st_prered, s->st_delta, s->st_f, s->st_gnorm, (int)s->st_cg, s->st_rnorm);
@@ -1876,6 +2091,9 @@ extern "C" double trmf_b200_stat(S *s, int32_t which) {
         case TRMF_STAT_COLLECTIVES: return (double)s->collectives;
         case TRMF_STAT_X_GRAM_MS: return s->ms_xg;
         case TRMF_STAT_FORMULATION: return s->cm_state > 0 ? 1.0 : 0.0;
+        case TRMF_STAT_CM_GRAM_MS: return s->ms_cmg;
+        case TRMF_STAT_CM_PRODUCT_MS: return s->ms_cmp;
+        case TRMF_STAT_CM_MISSING: return s->cm_state > 0 ? (double)(s->T * s->n - s->nnz) : 0.0;
     }
     return NAN;
 }
@@ -1971,7 +2189,9 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     if (!have_prev) cudaGetLastError();
     dev = have_prev ? prev_dev : 0;
     if (const char *e = getenv("TRMF_B200_DEVICE")) dev = atoi(e);
+    g_async_feed = !getenv("TRMF_B200_SYNC_FEED");      // (the caller's buffers stay valid until this call returns)
     S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, dev);
+    g_async_feed = false;
     if (!s) { if (have_prev) cudaSetDevice(prev_dev); return; }   // message already on stderr
     if (verbose > 0 && s->missing && f_kernel_choice(s->k, s->W) != F_KERNEL_MMA)
         fprintf(stderr, "[trmf-b200] note: k = %d is outside the tensor-core Gram kernels' ranks (or a factor is not 16-byte aligned): "
@@ -1984,7 +2204,9 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     trace_pt("train: returned");
     double t2 = now_ms();
     if (trace) { cudaStreamSynchronize(s->stream); t2 = now_ms(); }
+    if (trace) trace_dev(s->stream, "lag_val update done (train finished)");
     if (rc == 0) trmf_b200_download(s, pyW->val, pyH->val, pylag_val->val);
+    if (trace) { trace_dev(s->stream, "factors downloaded"); trace_dev_dump(); }
     const double t3 = now_ms();
     std::string keep = g_last_error;
     trmf_b200_destroy(s);

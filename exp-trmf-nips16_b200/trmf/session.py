@@ -14,7 +14,8 @@ from .rf_util import PyMatrix
 from .trmf import _clib
 
 STAT = dict(cg_iters=0, accepted=1, f=2, fnew=3, gnorm=4, kernel_launches=5,
-            f_ms=6, x_ms=7, lag_ms=8, f_kernel_ms=9, prered=10, actred=11, collectives=12, x_gram_ms=13, formulation=14)
+            f_ms=6, x_ms=7, lag_ms=8, f_kernel_ms=9, prered=10, actred=11, collectives=12, x_gram_ms=13, formulation=14,
+            cm_gram_ms=15, cm_product_ms=16, cm_missing=17)
 
 
 class SynthDesc(ctypes.Structure):

@@ -143,8 +143,12 @@ enum {
     TRMF_STAT_ACTRED = 11,
     TRMF_STAT_COLLECTIVES = 12,  /* NCCL collectives issued by this session so far            */
     TRMF_STAT_X_GRAM_MS = 13,    /* device ms of the Gram build (+ fused loss gradient) inside the last x_update */
-    TRMF_STAT_FORMULATION = 14   /* 1 = the session works over the MISSING cells of a mostly observed Y (csrc/complement.cuh),
+    TRMF_STAT_FORMULATION = 14,  /* 1 = the session works over the MISSING cells of a mostly observed Y (csrc/complement.cuh),
                                     0 = it walks the observed entries like the reference; decided at the first sparse update */
+    TRMF_STAT_CM_GRAM_MS = 15,   /* complement formulation, last whole-Y f_update: device ms of the Gram pass over the missing
+                                    cells (factor pre-split + the gather kernel) ...                                       */
+    TRMF_STAT_CM_PRODUCT_MS = 16,/* ... and of the fp64 tall-skinny product Y0^T W (split-K kernel + its finish)            */
+    TRMF_STAT_CM_MISSING = 17    /* number of missing cells the formulation walks (0 when it is off)                        */
 };
 double trmf_b200_stat(trmf_b200_session *s, int32_t which);
 /* Enable per-phase CUDA-event timing (off by default: it inserts stream syncs). */

@@ -97,8 +97,10 @@ def test_complement_path_can_be_forced_on_a_sparse_problem(monkeypatch):
 
 
 def test_complement_path_through_the_c_abi(monkeypatch):
-    """c_trmf_train with host buffers (slab-wise upload, host-packed indices): the complement F-update waits for every slab and
-    gives the factors of the device-resident session bit for bit."""
+    """c_trmf_train with host buffers (slab-wise upload, host-packed indices): the first complement F-update places and solves each
+    series slab as it lands (missing-cell lists, dense copy and per-time-stamp bitmaps built from the CSC slab; the by-time CSR is
+    never built) and still gives the factors of the device-resident session, which builds everything from the whole Y, bit for
+    bit: kernel shapes and split-K boundaries do not depend on how the series axis was cut."""
     from trmf.session import Session
     from oracle import abi
     lib = os.path.join(ROOT, "exp-trmf-nips16_b200", "trmf", "corelib", "trmf_float32.so")
