@@ -850,6 +850,7 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     return 0;
 }
 
+extern "C" void trmf_b200_feed_mode(int32_t async_feed) { g_async_feed = async_feed != 0; }
 extern "C" S *trmf_b200_create(const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size, const PyMatrix *W,
                                const PyMatrix *H, const PyMatrix *lag_val, int32_t missing, int32_t device) {
     S *s = new S();
@@ -2189,9 +2190,10 @@ extern "C" void c_trmf_train(const PyMatrix *pyY, uint32_t *py_lag_set, uint32_t
     if (!have_prev) cudaGetLastError();
     dev = have_prev ? prev_dev : 0;
     if (const char *e = getenv("TRMF_B200_DEVICE")) dev = atoi(e);
+    const bool feed_before = g_async_feed;
     g_async_feed = !getenv("TRMF_B200_SYNC_FEED");      // (the caller's buffers stay valid until this call returns)
     S *s = trmf_b200_create(pyY, py_lag_set, py_lag_size, pyW, pyH, pylag_val, missing, dev);
-    g_async_feed = false;
+    g_async_feed = feed_before;
     if (!s) { if (have_prev) cudaSetDevice(prev_dev); return; }   // message already on stderr
     if (verbose > 0 && s->missing && f_kernel_choice(s->k, s->W) != F_KERNEL_MMA)
         fprintf(stderr, "[trmf-b200] note: k = %d is outside the tensor-core Gram kernels' ranks (or a factor is not 16-byte aligned): "

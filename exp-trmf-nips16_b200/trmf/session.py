@@ -34,6 +34,8 @@ def _lib(dtype):
     P = POINTER(PyMatrix)
     lib.trmf_b200_create.restype = c_void_p
     lib.trmf_b200_create.argtypes = [P, POINTER(c_uint32), c_uint32, P, P, P, c_int32, c_int32]
+    lib.trmf_b200_feed_mode.restype = None
+    lib.trmf_b200_feed_mode.argtypes = [c_int32]
     lib.trmf_b200_create_device.restype = c_void_p
     lib.trmf_b200_create_device.argtypes = [c_uint64, c_uint64, c_uint64, c_uint32, c_void_p, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_void_p, POINTER(c_uint32), c_uint32,
@@ -100,8 +102,14 @@ class Session(object):
         self.T, self.k = self.pyW.py_buf["val"].shape
         self.n = self.pyH.py_buf["val"].shape[0]
         self.L = len(self.lag_set)
-        self.h = lib.trmf_b200_create(byref(self.pyY), self.lag_set.ctypes.data_as(POINTER(c_uint32)), self.L,
-                                      byref(self.pyW), byref(self.pyH), byref(self.pyL), int(bool(missing)), device)
+        # (self.pyY keeps Y's host buffers alive for the life of the session: the slab-wise upload of a large sparse Y may go on
+        #  on the library's feeder thread while the first update is already being enqueued)
+        lib.trmf_b200_feed_mode(1)
+        try:
+            self.h = lib.trmf_b200_create(byref(self.pyY), self.lag_set.ctypes.data_as(POINTER(c_uint32)), self.L,
+                                          byref(self.pyW), byref(self.pyH), byref(self.pyL), int(bool(missing)), device)
+        finally:
+            lib.trmf_b200_feed_mode(0)
         if not self.h:
             raise RuntimeError("trmf (CUDA) create failed: " + lib.trmf_b200_last_error().decode())
         self.set_params(lambdaI, lambdaAR, lambdaLag)

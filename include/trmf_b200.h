@@ -90,6 +90,12 @@ typedef struct trmf_b200_session trmf_b200_session;
 trmf_b200_session *trmf_b200_create(const PyMatrix *Y, const uint32_t *lag_set, uint32_t lag_size,
                                     const PyMatrix *W, const PyMatrix *H, const PyMatrix *lag_val,
                                     int32_t missing, int32_t device);
+/* By default trmf_b200_create has read everything it needs from Y's host buffers when it returns.  A caller that keeps those
+ * buffers alive and unchanged until its first trmf_b200_sync / trmf_b200_download (or trmf_b200_destroy) may set
+ * trmf_b200_feed_mode(1) on the creating thread: a large sparse Y is then packed and enqueued slab by slab on a feeder thread
+ * while the caller already enqueues the first update, which runs under the upload instead of behind it (what c_trmf_train does
+ * internally).  The mode is per thread and stays until changed; 0 restores the default. */
+void trmf_b200_feed_mode(int32_t async_feed);
 
 /* Create around arrays that ALREADY live in device memory (no copies; the
  * caller keeps ownership and must keep them alive).  Sparse Y only: by-time

@@ -117,3 +117,34 @@ def test_complement_path_through_the_c_abi(monkeypatch):
     Wo, Ho, Lo = tn.train(Y.astype(np.float64), p["lags"], f32(p["W0"]).astype(np.float64), f32(p["H0"]).astype(np.float64),
                           f32(p["L0"]).astype(np.float64), **kw)
     assert cases.rel(H, Ho) < 3e-5 and cases.rel(W, Wo) < 3e-5 and cases.rel(L, Lo) < 3e-5      # (two chained iterations)
+
+
+def test_host_buffer_call_with_a_series_the_bitmaps_cannot_carry(monkeypatch):
+    """Slab-wise upload where a series in a LATE slab has its entries in descending row order (legal for the reference's core,
+    which never looks at the order): the feeder thread has already published the earlier slabs as bitmaps when the packer
+    declines that series, falls back to plain row indices for the rest, and the consumer switches from the inverted-bitmap
+    expansion to the bitmap built from the indices.  Nothing in the complement formulation depends on the order of a series'
+    entries, so the factors equal those of the sorted input bit for bit."""
+    from oracle import abi
+    for name in ("TRMF_B200_COMPLEMENT", "TRMF_B200_SYNC_FEED"):
+        monkeypatch.delenv(name, raising=False)
+    lib = os.path.join(ROOT, "exp-trmf-nips16_b200", "trmf", "corelib", "trmf_float32.so")
+    p = _problem(2600, 2000, 40, [1, 7, 24], 0.9, seed=5)
+    Y = sps.csr_matrix((f32(p["Ysp"].data), p["Ysp"].indices, p["Ysp"].indptr), shape=p["Ysp"].shape)
+    assert Y.nnz >= 1 << 22
+    kw = dict(lambdaI=0.5, lambdaAR=50.0, lambdaLag=0.5, max_iter=2, period_Lag=1, missing=True)
+    args = (p["lags"], f32(p["W0"]), f32(p["H0"]), f32(p["L0"]))
+    ref = abi.run_train(lib, abi.HostMatrix(Y, np.float32), *args, dtype=np.float32, **kw)
+    for j in (1400, 5):          # a series of the sixth slab of eight; a series of the first slab
+        hY = abi.HostMatrix(Y, np.float32)
+        e0, e1 = int(hY.bufs["col_ptr"][j]), int(hY.bufs["col_ptr"][j + 1])
+        assert e1 - e0 > 100
+        hY.bufs["row_idx"][e0:e1] = hY.bufs["row_idx"][e0:e1][::-1].copy()
+        hY.bufs["val"][e0:e1] = hY.bufs["val"][e0:e1][::-1].copy()
+        got = abi.run_train(lib, hY, *args, dtype=np.float32, **kw)
+        for a, b in zip(got, ref):
+            assert np.array_equal(a, b), j
+    monkeypatch.setenv("TRMF_B200_SYNC_FEED", "1")      # the same call without the feeder thread
+    got = abi.run_train(lib, abi.HostMatrix(Y, np.float32), *args, dtype=np.float32, **kw)
+    for a, b in zip(got, ref):
+        assert np.array_equal(a, b)
