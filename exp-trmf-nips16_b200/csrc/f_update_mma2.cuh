@@ -575,8 +575,17 @@ static inline int f_update_mma2_launch(cudaStream_t st, int num_sms, const uint6
     } while (0)
 #define FM2_CASE(KK, NWIDE, MINBB)                                                                              \
     case KK:                                                                                                    \
-        if (wide) FM2_LAUNCH(KK, NWIDE, 1); else FM2_LAUNCH(KK, 4, MINBB);                                      \
+        if (wide) FM2_LAUNCH(KK, NWIDE, 1);                                                                     \
+        else if constexpr (MODE == fm::MODE_GONLY) {                                                            \
+            if (gonly_nw == 2) FM2_LAUNCH(KK, 2, 2 * MINBB); else FM2_LAUNCH(KK, 4, MINBB);                     \
+        } else FM2_LAUNCH(KK, 4, MINBB);                                                                        \
         break;
+    // rows of the complement lists are short (~1000 cells at C2 against ~9000 observed ones): a row goes to two warps instead of
+    // four (twice the rows in flight per SM, half the partials to add per row) -- 0.368 -> 0.351 ms per pass at C2, C3's X-update
+    // 0.947 -> 0.908 ms; TRMF_B200_GONLY_WARPS=4 restores the four-warp CTAs
+    int gonly_nw = 2;
+    if (const char *e = getenv("TRMF_B200_GONLY_WARPS")) gonly_nw = atoi(e);
+    (void)gonly_nw;
     switch (k) {
         FM2_CASE(8, 16, 4) FM2_CASE(12, 16, 4) FM2_CASE(16, 16, 4) FM2_CASE(20, 16, 4) FM2_CASE(24, 16, 4) FM2_CASE(28, 16, 4)
         FM2_CASE(32, 16, 4) FM2_CASE(36, 16, 4) FM2_CASE(40, 16, 4)

@@ -24,12 +24,18 @@ TMO=120 run ${tag}_smoke python -c "import __graft_entry__ as g; g.smoke()"
 timeout 400 python bench.py > "$out/${tag}_bench_c2_n1.json" 2> "$out/${tag}_bench_c2_n1.err"; cut -c1-300 "$out/${tag}_bench_c2_n1.json"
 timeout 300 python bench.py --config c3 --strong none > "$out/${tag}_bench_c3_n1.json" 2> "$out/${tag}_bench_c3_n1.err"
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$out/${tag}_bench_c2_reference_arm.json" 2> "$out/${tag}_bench_c2_reference_arm.err"
+TRMF_B200_TRACE=1 timeout 200 python bench.py --steps 3 --warmup 3 --no-parity --strong none --no-cpu-baseline > /dev/null 2> "$out/${tag}_trace_c2_host_buffer_call.txt"
+python tools/h2d_probe.py >> "$out/${tag}_trace_c2_host_buffer_call.txt" 2>&1
 for cfg in electricity traffic; do
     timeout 200 python tools/rolling_bench.py --config "$cfg" --repeat 2 > "$out/${tag}_rolling_$cfg.json" 2> "$out/${tag}_rolling_$cfg.err"; cat "$out/${tag}_rolling_$cfg.json"
 done
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file "$out/${tag}_launches_c2.csv" \
     python bench.py --steps 2 --warmup 1 --no-e2e --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_launches.log" 2>&1
 python tools/ncu_summary.py "$out/${tag}_launches_c2.csv" > "$out/${tag}_launches_c2.txt"; head -14 "$out/${tag}_launches_c2.txt"
+# the same with the host-buffer arm (c_trmf_train: per-slab placement / Gram / product / solve kernels of the first F-update)
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 4000 --csv --log-file "$out/${tag}_launches_c2_e2e.csv" \
+    python bench.py --steps 1 --warmup 1 --no-parity --strong none --no-cpu-baseline > "$out/${tag}_ncu_launches_e2e.log" 2>&1
+python tools/ncu_summary.py "$out/${tag}_launches_c2_e2e.csv" > "$out/${tag}_launches_c2_e2e.txt"
 fi
 
 if [ "$mode" = "full" ] || [ "$mode" = "ncu" ]; then
