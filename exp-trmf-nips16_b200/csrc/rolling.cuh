@@ -190,6 +190,10 @@ static int roll_create_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         const bool have_csr = dense_to_sparse || (Y->row_ptr && (nnz == 0 || (Y->col_idx && Y->val_t)));
         const bool have_csc = !dense_to_sparse && Y->col_ptr && (nnz == 0 || (Y->row_idx && Y->val));
         if (!have_csr && !have_csc) return fail("sparse Y carries neither a complete CSR nor a complete CSC half");
+        // may the complement formulation be used on the windows (cm_on)?  Not if some cell occurs twice in Y.
+        s->idx_strict = dense_to_sparse ? true
+                        : (sizeof(V) == 4 && s->missing) ? (have_csc ? host_lists_strict(Y->col_ptr, Y->row_idx, s->n) : host_lists_strict(Y->row_ptr, Y->col_idx, s->T))
+                                                         : false;
         if (dev_alloc(&s->col_idx, nnz) || dev_alloc(&s->R_val_t, nnz) ||
             dev_alloc(&s->R_col_ptr, s->n + 1) || dev_alloc(&s->R_row_idx, nnz) || dev_alloc(&s->R_val, nnz) ||
             dev_alloc(&s->col_ptr, s->n + 1) || dev_alloc(&s->row_idx, nnz) || dev_alloc(&s->val, nnz))

@@ -179,6 +179,11 @@ struct trmf_b200_session {
     uint32_t *cm_bm0 = nullptr;       // while the lists are built: per series, bitmap of its missing time stamps ...
     uint32_t *cm_bmT = nullptr;       // ... and per time stamp, bitmap of its missing series
     size_t cm_placed = 0;             // the series [0, cm_placed) are in cm_idx[0], cm_Y0 and cm_bmT
+    // The formulation counts every cell of a row once, so it may only be used when no cell occurs twice in Y (duplicates are
+    // legal input: the reference treats them as separate observations, rf_util.py:100-119).  Known where Y comes in: host index
+    // lists are scanned for strict ascent (by the bitmap packer, or host_lists_strict), bitmaps and dense arrays cannot hold
+    // duplicates, device-resident arrays are canonical by the API's contract.
+    bool idx_strict = false;
     bool cm_ready = false;            // by-time list and cm_yy are built
     double *frow = nullptr;           // per-time-stamp loss values of the fused Gram + gradient kernel (T)
     double *sys = nullptr;            // F-update: assembled fp64 systems of one batch of series, solved by chol_solve_kernel
@@ -432,6 +437,31 @@ static bool pack_one_series(const uint32_t *r, size_t cnt, uint32_t *w, uint32_t
     pack_series_scalar(r, cnt, w);
     return true;
 }
+// every index list of a compressed sparse half strictly ascending?  (host arrays; up to 8 threads for large inputs)
+static bool host_lists_strict(const uint64_t *ptr, const uint32_t *idx, uint64_t nlists) {
+    if (!ptr || !idx) return false;
+    auto range_ok = [&](uint64_t l0, uint64_t l1) {
+        for (uint64_t l = l0; l < l1; ++l) {
+            const uint32_t *r = idx + ptr[l];
+            const size_t cnt = (size_t)(ptr[l + 1] - ptr[l]);
+#if defined(__x86_64__)
+            if (__builtin_cpu_supports("avx2")) { if (!ascending_avx2(r, cnt)) return false; continue; }
+#endif
+            for (size_t i = 0; i + 1 < cnt; ++i) if (!(r[i] < r[i + 1])) return false;
+        }
+        return true;
+    };
+    const uint64_t nnz = ptr[nlists];
+    unsigned nt = nnz >= (1u << 22) ? std::min(8u, std::max(1u, std::thread::hardware_concurrency())) : 1u;
+    if (nt <= 1) return range_ok(0, nlists);
+    std::vector<char> ok(nt, 1);
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t)
+        th.emplace_back([&, t]() { ok[t] = range_ok(nlists * t / nt, nlists * (t + 1) / nt) ? 1 : 0; });
+    for (auto &x : th) x.join();
+    for (char c : ok) if (!c) return false;
+    return true;
+}
 // The index bitmaps of all series, packed by the host cores IN SLAB ORDER while the calling thread waits for slab after slab and
 // hands each to `slab_done(b)` (which enqueues its copies): the first F-update launch only waits for the first slab's bitmap and
 // values, and the copy engine never idles behind the packing.  slab_j = series bounds of the slabs.  Returns false when some
@@ -653,6 +683,7 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
     if (s->k < 1 || s->k > 128) return fail("rank k = %d outside the supported range 1..128", s->k);
     if (check_lags(s, lag_set, lag_size)) return 1;
     const bool bitmap = Y->type == TRMF_SPARSE_BITMAP;
+    s->idx_strict = bitmap;      // (plain index lists: settled below, where the upload path is chosen)
     if (Y->type == TRMF_SPARSE || bitmap) {
         s->sparse_storage = true;
         s->nnz = Y->nnz;
@@ -681,7 +712,10 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         const bool have_host_csr = !bitmap && Y->row_ptr && (s->nnz == 0 || (Y->col_idx && Y->val_t));
         const bool have_host_csc = Y->col_ptr && (s->nnz == 0 || (Y->row_idx && Y->val));
         if (!have_host_csc && !have_host_csr) return fail("sparse Y carries neither a complete CSR nor a complete CSC half");
+        // would the complement formulation be considered at all (cm_on)?  Only then is it worth knowing whether the lists are strict
+        const bool cm_candidate = sizeof(V) == 4 && s->missing && (double)s->nnz >= 0.7 * (double)s->T * (double)s->n;
         if (!have_host_csc) {
+            if (cm_candidate) s->idx_strict = host_lists_strict(Y->row_ptr, Y->col_idx, s->T);
             // CSR-only PyMatrix (trmf.rf_util.PyMatrix(..., twin=False) of a csr_matrix): upload it and derive the
             // by-series CSC on the device -- the same stable transpose with the roles of rows and columns swapped
             if (h2d_new(s, &s->row_ptr, Y->row_ptr, s->T + 1) || h2d_new(s, &s->col_idx, Y->col_idx, s->nnz) ||
@@ -716,6 +750,9 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
             }
             dev_free(bm_dev);
         }
+        // plain index lists that the packer will not look at: scan them here (the packer's own check covers the host-packed path:
+        // a declined series flips the session to the walk in cm_f_update)
+        if (!bitmap && cm_candidate) s->idx_strict = host_pack ? true : host_lists_strict(Y->col_ptr, Y->row_idx, s->n);
         if (!slabs) {
             if (!bitmap && h2d_new(s, &s->row_idx, Y->row_idx, s->nnz)) return 1;
             if (h2d_new(s, &s->val, Y->val, s->nnz)) return 1;
@@ -888,6 +925,7 @@ extern "C" S *trmf_b200_create_device(uint64_t T, uint64_t n, uint64_t nnz, uint
     s->col_ptr = const_cast<uint64_t *>(d_col_ptr); s->row_idx = const_cast<uint32_t *>(d_row_idx);
     s->val = (V *)const_cast<void *>(d_val);
     s->W = (V *)d_W; s->H = (V *)d_H; s->th = (V *)d_lag_val;
+    s->idx_strict = true;      // the API's contract: canonical CSR / CSC (strictly ascending index lists, no cell twice)
     return s;
 }
 
@@ -1344,6 +1382,8 @@ static int gram_hv_launch(S *s, const V *d, V *Hd, bool want_dhd, const int *gat
 // --------------------------------------------------------------------------
 #ifdef TRMF_F32
 static int need_csr(S *s);
+static int mma_f_range(S *s, size_t j0, size_t j1, bool rescale);
+static void cm_reset(S *s);
 static bool cm_supported_k(int k) { return f_update_mma_supported(k); }
 // decided once per session: a sparse session of the mma2 kernel family whose Y observes >= 70 % of its cells and whose
 // dense copy fits comfortably.  TRMF_B200_COMPLEMENT=0 / 1 pins the choice (1 still needs the kernel family).
@@ -1353,6 +1393,7 @@ static bool cm_on(S *s) {
     const char *e = getenv("TRMF_B200_COMPLEMENT");
     if (e && atoi(e) == 0) return false;
     if (!s->missing || !s->sparse_storage || !use_mma2() || use_tc(s->k) || !cm_supported_k(s->k)) return false;
+    if (!s->idx_strict) return false;      // some cell may occur twice: only the walk counts it twice, like the reference
     if (f_kernel_choice(s->k, s->W) != F_KERNEL_MMA || f_kernel_choice(s->k, s->H) != F_KERNEL_MMA) return false;
     if (s->T >= (1ull << 32) || s->n >= (1ull << 32) || s->T == 0 || s->n == 0) return false;
     const double cells = (double)s->T * (double)s->n;
@@ -1560,6 +1601,17 @@ static int cm_f_update(S *s) {
     for (size_t b = 0; b + 1 < s->slab_j.size(); ++b) {
         const size_t j0 = s->slab_j[b], j1 = s->slab_j[b + 1];
         if (slab_wait(s, b)) return 1;
+        if (s->feed_plain_from != (size_t)-1 && b >= s->feed_plain_from) {
+            // the packer declined a series of this slab: its index list is not strictly ascending -- unsorted, or the same cell
+            // twice.  The formulation is dropped for good and every series is (re)done by the walk over the observed entries.
+            cm_reset(s);
+            s->cm_state = -1;
+            s->idx_strict = false;
+            if (getenv("TRMF_B200_VERBOSE"))
+                fprintf(stderr, "[trmf-b200] note: row indices of some series are not strictly ascending (unsorted or duplicate "
+                                "cells): walking the observed entries instead of the complement\n");
+            return wait_slabs(s) || mma_f_range(s, 0, s->n, true);
+        }
         if (b < 2) trace_pt("F-update: slab published, enqueueing its kernels");
         if (expand_slab_bitmaps(s, j0, j1)) return 1;
         if (b == 0) trace_dev(s->stream, "F-update: slab 0 expanded (scratch zeroed before it)");
@@ -1774,6 +1826,15 @@ extern "C" int trmf_b200_x_update(S *s) {
     // The by-time CSR serves the walks over Omega.  The complement formulation with per-time-stamp Grams (Gram build, gradient,
     // objective, Hessian products and f(w + s) all come from the Grams) never touches it: a host-buffer session on that path does
     // not even build it.
+    if (s->slabs_pending && s->feeder.joinable()) {
+        // no F-update has consumed the upload yet: let the feeder finish, it may have found index lists the formulation cannot take
+        s->feeder.join();
+        if (s->feed_plain_from != (size_t)-1) {
+            s->idx_strict = false;
+            if (s->cm_state > 0) cm_reset(s);
+            s->cm_state = 0;
+        }
+    }
     bool csr_free = s->missing && cm_on(s) && !getenv("TRMF_B200_NO_FUSED_GRAD") && !getenv("TRMF_B200_WALK_FNEW") &&
                     !getenv("TRMF_B200_NO_GRAM_HV");
     if (csr_free) {

@@ -99,7 +99,10 @@ void trmf_b200_feed_mode(int32_t async_feed);
 
 /* Create around arrays that ALREADY live in device memory (no copies; the
  * caller keeps ownership and must keep them alive).  Sparse Y only: by-time
- * CSR (row_ptr/col_idx/val_t) and by-series CSC (col_ptr/row_idx/val).
+ * CSR (row_ptr/col_idx/val_t) and by-series CSC (col_ptr/row_idx/val).  Both
+ * halves must be canonical -- index lists strictly ascending, no cell twice (what
+ * scipy's conversions and csr_from_csc produce): a mostly observed Y is solved over
+ * its MISSING cells, which counts every cell once.
  * `n_total`/`col_offset`: this rank's slab [col_offset, col_offset+n) of a
  * global series axis of n_total (single GPU: n_total = n, col_offset = 0). */
 trmf_b200_session *trmf_b200_create_device(uint64_t T, uint64_t n, uint64_t nnz, uint32_t k,
