@@ -700,7 +700,8 @@ def run_e2e(args, cfg, torch, dist, lib, s_dev, sd, dtype, rank, world, local_ra
     nbytes = {name: pm.py_buf[name].nbytes for name in copied}
     bm_bytes = n_loc * ((T + 31) // 32) * 4
     host_pack = ("row_idx" in nbytes and not os.environ.get("TRMF_B200_HOST_CSR") and not os.environ.get("TRMF_B200_NO_HOST_PACK")
-                 and nnz_loc >= (1 << 22) and n_loc >= 16 and bm_bytes <= nnz_loc)
+                 and nnz_loc >= (1 << 22) and n_loc >= 16 and bm_bytes <= nnz_loc
+                 and (lib.trmf_b200_pack_threads() >= 4 or os.environ.get("TRMF_B200_PACK_THREADS")))
     if host_pack:
         nbytes["row_idx"] = bm_bytes
     h2d = sum(nbytes.values()) + W0.nbytes + H0.nbytes + L0.nbytes

@@ -466,13 +466,17 @@ static bool host_lists_strict(const uint64_t *ptr, const uint32_t *idx, uint64_t
 // hands each to `slab_done(b)` (which enqueues its copies): the first F-update launch only waits for the first slab's bitmap and
 // values, and the copy engine never idles behind the packing.  slab_j = series bounds of the slabs.  Returns false when some
 // series cannot be carried by a bitmap (slab_done may already have been called for earlier slabs) or slab_done failed (*rc = 1).
-template <class F>
-static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, const std::vector<size_t> &slab_j, uint32_t words,
-                              uint64_t rows, uint32_t *out, F slab_done, int *rc) {
+// threads a host-buffer call may use for packing (packers + the coordinating thread)
+static unsigned pack_thread_budget() {
     unsigned nt = std::thread::hardware_concurrency();
     if (const char *e = getenv("LOCAL_WORLD_SIZE")) nt /= (unsigned)std::max(1, atoi(e));   // one process per GPU: share the host cores
     if (const char *e = getenv("TRMF_B200_PACK_THREADS")) nt = (unsigned)std::max(1, atoi(e));
-    nt = std::max(2u, std::min(nt, 32u));      // (nt - 1 packers + the calling thread)
+    return std::max(2u, std::min(nt, 32u));
+}
+template <class F>
+static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, const std::vector<size_t> &slab_j, uint32_t words,
+                              uint64_t rows, uint32_t *out, F slab_done, int *rc) {
+    unsigned nt = pack_thread_budget();        // (nt - 1 packers + the calling thread)
     // on a feeder thread the session's calling thread is busy enqueueing kernels at the same time: leave it a core
     if (g_on_feeder && !getenv("TRMF_B200_PACK_THREADS") && nt > 4) nt -= 1;
     const bool polite = g_on_feeder;
@@ -734,8 +738,11 @@ static int create_host_impl(S *s, const PyMatrix *Y, const uint32_t *lag_set, ui
         // Caller sent plain row indices of a mostly-observed matrix: pack them into bitmaps on the host cores (see pack_bitmap_host)
         // instead of pushing 4 bytes per entry over PCIe.  Worth it when the bitmaps are at most 1/4 of the index bytes.
         const uint32_t bm_words = (uint32_t)((s->T + 31) / 32);
+        // ... and when there are host cores to pack with: a packer does 0.65 ns per entry, the 4 bytes it saves cross PCIe in
+        // 0.08-0.2 ns -- with fewer than three packers (8 ranks sharing 16 cores) the plain indices arrive sooner.  Measured per
+        // rank at C2 (ms per host-buffer session): N = 1 (15 packers) 10.4, N = 2 (7) 11.9, N = 4 (3) 20.7 against 33.6 plain.
         const bool host_pack = !bitmap && slabs && s->T < (1ull << 32) && (size_t)s->n * bm_words * 4 <= s->nnz &&
-                               !getenv("TRMF_B200_NO_HOST_PACK");
+                               !getenv("TRMF_B200_NO_HOST_PACK") && (pack_thread_budget() >= 4 || getenv("TRMF_B200_PACK_THREADS"));
         uint32_t *bm_dev = nullptr;
         if (bitmap) {
             // the row indices travel as one bitmap per series (cols x ceil(T/32) words) and are expanded here, on the session
@@ -2164,6 +2171,7 @@ extern "C" double trmf_b200_stat(S *s, int32_t which) {
 // library info
 // --------------------------------------------------------------------------
 extern "C" int trmf_b200_value_bytes(void) { return (int)sizeof(V); }
+extern "C" int trmf_b200_pack_threads(void) { return (int)pack_thread_budget(); }
 extern "C" const char *trmf_b200_version(void) { return TRMF_B200_VERSION; }
 extern "C" const char *trmf_b200_last_error(void) { return g_last_error.c_str(); }
 extern "C" int trmf_b200_device_count(void) {

@@ -76,6 +76,9 @@ int         trmf_b200_value_bytes(void);        /* 4 or 8: sizeof(ValueType) of 
 const char *trmf_b200_version(void);
 const char *trmf_b200_last_error(void);         /* "" when the last call on this thread succeeded */
 int         trmf_b200_device_count(void);       /* <= 0: no usable CUDA device */
+/* Host threads a host-buffer session may use to pack row indices into bitmaps (cores / LOCAL_WORLD_SIZE, TRMF_B200_PACK_THREADS);
+ * below 4 the plain indices are uploaded instead. */
+int         trmf_b200_pack_threads(void);
 
 /* ---- device-resident session (additive) ----
  * A session owns Y (both orientations), the factors and all work vectors in
