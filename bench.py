@@ -15,9 +15,12 @@ T x k partial.
 
 Printed JSON (rank 0, one line): value = device-resident throughput (Y already in
 HBM), e2e = the same step through the public host-buffer API (H2D of Y and factors,
-D2H of the factors inside the timed region), roofline = the F-update kernel against
-the measured HBM peak, cpu_baseline = the reference's own OpenMP solver
-(oracle/_ref, built from /root/reference by oracle/Makefile) on a bounded sample.
+D2H of the factors inside the timed region), roofline = the F-update's gather kernel against
+the measured HBM peak (walk over the observed entries: SURVEY 8d's bytes per observed entry;
+complement formulation: per walked MISSING cell, with roofline_product = its fp64 tall-skinny
+product against the measured DMMA issue rate), roofline_x = the X-update's Gram build,
+cpu_baseline = the reference's own OpenMP solver (oracle/_ref, built from /root/reference by
+oracle/Makefile) on the whole workload (C2) or a labelled sample (C4 / C5).
 """
 import argparse
 import ctypes

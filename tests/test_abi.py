@@ -38,6 +38,24 @@ def test_library_exports_every_declared_symbol(lib):
     assert dll.trmf_b200_value_bytes() == (4 if "32" in lib else 8)
 
 
+def test_pack_thread_budget_follows_the_ranks_on_the_host(monkeypatch):
+    """csrc/trmf_b200.cu:pack_thread_budget -- host threads a host-buffer session packs row indices with: the cores divided by
+    LOCAL_WORLD_SIZE (one process per GPU shares the host), TRMF_B200_PACK_THREADS pins it, never below 2 (one packer + the
+    coordinating thread) nor above 32; below 4 the session uploads plain indices instead of packing."""
+    dll = ctypes.CDLL(os.path.join(CORELIB, "trmf_float32.so"))
+    dll.trmf_b200_pack_threads.restype = ctypes.c_int
+    for name in ("LOCAL_WORLD_SIZE", "TRMF_B200_PACK_THREADS"):
+        monkeypatch.delenv(name, raising=False)
+    cores = os.cpu_count() or 1
+    assert dll.trmf_b200_pack_threads() == max(2, min(cores, 32))
+    monkeypatch.setenv("LOCAL_WORLD_SIZE", "8")
+    assert dll.trmf_b200_pack_threads() == max(2, min(cores // 8, 32))
+    monkeypatch.setenv("TRMF_B200_PACK_THREADS", "5")
+    assert dll.trmf_b200_pack_threads() == 5
+    monkeypatch.setenv("TRMF_B200_PACK_THREADS", "100")
+    assert dll.trmf_b200_pack_threads() == 32
+
+
 def test_pymatrix_layout_is_the_reference_pod():
     # rf_util.py:41-52 / rf_matrix.h:3407-3415: 80 bytes, fixed offsets
     assert ctypes.sizeof(PyMatrix) == 80
