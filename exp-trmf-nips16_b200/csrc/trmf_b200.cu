@@ -401,6 +401,51 @@ __attribute__((target("avx2,popcnt"))) static void pack_series_words(const uint3
         p += taken;
     }
 }
+// The same for NS series in lock step, with the strict-ascent check folded in.  One series alone is bound by the latency of its
+// dependency chain (position -> load -> compare -> movemask -> popcount -> position: ~50 clk per word) and, with the ascent check
+// as a pass of its own, reads the index array twice -- a packer thread is then bound by what one core can stream (~10 GB/s on
+// the build container's host: 0.87 ns per entry for the two passes).  NS independent chains fill the pipeline and the one pass
+// halves the bytes.  Every pair (i, i + 1) of a series lies in some window [p, p + 32] the loop visits, so comparing each window
+// position with its successor (signed: indices below 2^31, see the caller) covers them all.  Every series' words are all written
+// (no memset needed); r[s] must be readable up to r[s][cnt[s] + 32].  Returns false when some series is not strictly ascending.
+template <int NS>
+__attribute__((target("avx2,popcnt"))) static bool pack_series_words_multi(const uint32_t *const *r, const size_t *cnt, uint32_t *const *w,
+                                                                           uint32_t words) {
+    const __m256i one = _mm256_set1_epi32(1), m31 = _mm256_set1_epi32(31);
+    const __m256i lane = _mm256_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7);
+    size_t p[NS];
+    __m256i badv = _mm256_setzero_si256();
+    for (int q = 0; q < NS; ++q) p[q] = 0;
+    for (uint32_t wi = 0; wi < words; ++wi) {
+        const __m256i wv = _mm256_set1_epi32((int)wi);
+#pragma GCC unroll 8
+        for (int q = 0; q < NS; ++q) {
+            const long long left = (long long)(cnt[q] - p[q]);
+            const __m256i leftv = _mm256_set1_epi32((int)(left > 64 ? 64 : left));
+            __m256i acc = _mm256_setzero_si256();
+            unsigned taken = 0;
+#pragma GCC unroll 4
+            for (int v = 0; v < 4; ++v) {
+                const __m256i pos = _mm256_add_epi32(lane, _mm256_set1_epi32(8 * v));
+                const __m256i idx = _mm256_loadu_si256((const __m256i *)(r[q] + p[q] + 8 * v));
+                const __m256i nxt = _mm256_loadu_si256((const __m256i *)(r[q] + p[q] + 8 * v + 1));
+                const __m256i in = _mm256_and_si256(_mm256_cmpeq_epi32(_mm256_srli_epi32(idx, 5), wv), _mm256_cmpgt_epi32(leftv, pos));
+                // pair (pos, pos + 1) exists iff pos + 1 < left; it is in order iff nxt > idx
+                const __m256i pair = _mm256_cmpgt_epi32(leftv, _mm256_add_epi32(pos, one));
+                badv = _mm256_or_si256(badv, _mm256_andnot_si256(_mm256_cmpgt_epi32(nxt, idx), pair));
+                acc = _mm256_or_si256(acc, _mm256_and_si256(_mm256_sllv_epi32(one, _mm256_and_si256(idx, m31)), in));
+                taken += (unsigned)__builtin_popcount((unsigned)_mm256_movemask_ps(_mm256_castsi256_ps(in)));
+            }
+            w[q][wi] = pack_hor_avx2(acc);
+            p[q] += taken;
+        }
+    }
+    // Windows [p, p + 32] tile the whole list only if every entry was consumed (an entry beyond the last word, or out of order,
+    // stalls its series): both conditions together say "strictly ascending and inside the bitmap".
+    bool all = true;
+    for (int q = 0; q < NS; ++q) all &= p[q] == cnt[q];
+    return all && _mm256_testz_si256(badv, badv) != 0;
+}
 // strictly ascending?  (signed compares: the caller guarantees indices below 2^31)
 __attribute__((target("avx2"))) static bool ascending_avx2(const uint32_t *r, size_t cnt) {
     __m256i ok = _mm256_set1_epi32(-1);
@@ -500,7 +545,30 @@ static bool pack_bitmap_slabs(const uint64_t *col_ptr, const uint32_t *row_idx, 
         for (;;) {
             const size_t c = next.fetch_add(1);
             if (c >= chunks.size() || bad.load(std::memory_order_relaxed)) return;
-            for (size_t j = chunks[c].j0; j < chunks[c].j1; ++j)
+            size_t j = chunks[c].j0;
+#if defined(__x86_64__)
+            // four series at a time (pack_series_words_multi) while all four may be read 32 entries past their end
+            while (avx2 && algo == 0 && rows < (1ull << 31) && j + 4 <= chunks[c].j1 && col_ptr[j + 4] + 33 <= nnz_all) {
+                const uint32_t *r4[4];
+                size_t c4[4];
+                uint32_t *w4[4];
+                for (int q = 0; q < 4; ++q) {
+                    r4[q] = row_idx + col_ptr[j + q];
+                    c4[q] = (size_t)(col_ptr[j + q + 1] - col_ptr[j + q]);
+                    w4[q] = out + (j + q) * (size_t)words;
+                    if (c4[q] && (uint64_t)r4[q][c4[q] - 1] >= rows) {
+                        bad.store(true);
+                        return;
+                    }
+                }
+                if (!pack_series_words_multi<4>(r4, c4, w4, words)) {      // some series not strictly ascending
+                    bad.store(true);
+                    return;
+                }
+                j += 4;
+            }
+#endif
+            for (; j < chunks[c].j1; ++j)
                 if (!pack_one_series(row_idx + col_ptr[j], (size_t)(col_ptr[j + 1] - col_ptr[j]), out + j * (size_t)words, words, rows, avx2,
                                      col_ptr[j + 1] + 32 <= nnz_all, algo)) {
                     bad.store(true);

@@ -292,3 +292,22 @@ def test_host_packing_of_row_indices_matches_the_numpy_mask():
         cp = np.array([0, len(bad)], dtype=np.uint64)
         rc, _ = run(T, cp, np.ascontiguousarray(bad, dtype=np.uint32))
         assert rc == 1
+        # ... and the same series among eleven good ones: four series are packed in lock step there, with the ascent check folded
+        # into the packing pass (pack_series_words_multi)
+        for where in (0, 2, 3, 5):
+            group = [base.copy() for _ in range(12)]
+            group[where] = np.ascontiguousarray(bad, dtype=np.uint32)
+            cp = np.r_[0, np.cumsum([len(x) for x in group])].astype(np.uint64)
+            rc, _ = run(T, cp, np.concatenate(group).astype(np.uint32))
+            assert rc == 1, where
+    # an out-of-range index in the MIDDLE of an otherwise ascending series (the last one is in range), empty series inside a group
+    group = [base.copy() for _ in range(12)]
+    group[1] = np.r_[base[:300], 5000, base[300:]].astype(np.uint32)
+    cp = np.r_[0, np.cumsum([len(x) for x in group])].astype(np.uint64)
+    rc, _ = run(T, cp, np.concatenate(group).astype(np.uint32))
+    assert rc == 1
+    group = [base.copy(), np.zeros(0, dtype=np.uint32), np.arange(5, 1000, 7, dtype=np.uint32), np.zeros(0, dtype=np.uint32)] + [base.copy() for _ in range(8)]
+    cp = np.r_[0, np.cumsum([len(x) for x in group])].astype(np.uint64)
+    ri = np.concatenate(group).astype(np.uint32)
+    rc, out = run(T, cp, ri)
+    assert rc == 0 and np.array_equal(out, pack_bitmap(cp, ri, T))
