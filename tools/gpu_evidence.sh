@@ -21,6 +21,7 @@ run() { local name="$1"; shift; echo "== $name: $*"; ( time timeout "${TMO:-300}
 if [ "$mode" != "ncu" ]; then
 TMO=900 run ${tag}_gpu_tests python -m pytest tests -m gpu -q -x --durations=8
 TMO=120 run ${tag}_smoke python -c "import __graft_entry__ as g; g.smoke()"
+TMO=120 run ${tag}_slab_sanity python tools/slab_sanity.py
 timeout 400 python bench.py > "$out/${tag}_bench_c2_n1.json" 2> "$out/${tag}_bench_c2_n1.err"; cut -c1-300 "$out/${tag}_bench_c2_n1.json"
 timeout 300 python bench.py --config c3 --strong none > "$out/${tag}_bench_c3_n1.json" 2> "$out/${tag}_bench_c3_n1.err"
 timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > "$out/${tag}_bench_c2_reference_arm.json" 2> "$out/${tag}_bench_c2_reference_arm.err"
